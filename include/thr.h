@@ -1,0 +1,198 @@
+/*
+ * thr.h — C-ABI of libthr.so: the B200-native triple-hybrid retrieval scoring path.
+ *
+ * This is the drop-in boundary below the reference's Python retriever.  Every entry
+ * point replaces the arithmetic behind one reference call site (cited per function,
+ * paths relative to the reference checkout).  The reference itself has no FFI: its
+ * scoring lives in Postgres RPCs and an HTTP reranker, so the binding a maintainer
+ * adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only, no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer on the handle's GPU unless the name starts
+ *     with `h_`.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - Every call returns 0 (THR_OK) or a negative THR_E* code; thr_last_error()
+ *     returns a human-readable message for the most recent failure on that handle.
+ *   - Calls enqueue work on `stream` and return; device-side failures (candidate
+ *     buffer overflow, pipeline watchdog) are reported by thr_sync().
+ *   - A handle is thread-compatible: one thread at a time per handle, no globals.
+ *   - There is NO CPU fallback anywhere behind this interface.
+ */
+#ifndef THR_H_
+#define THR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THR_ABI_VERSION 1
+
+enum {
+  THR_OK = 0,
+  THR_EINVAL = -1,       /* bad argument */
+  THR_ECUDA = -2,        /* CUDA runtime / driver error */
+  THR_EUNSUPPORTED = -3, /* shape outside what the sm_100a kernels are built for */
+  THR_ENOINDEX = -4,     /* a *_topk call before the matching *_index_set */
+  THR_EOVERFLOW = -5,    /* device candidate buffer overflowed (reported by thr_sync) */
+  THR_ETIMEOUT = -6,     /* device pipeline watchdog fired (reported by thr_sync) */
+  THR_ENOMEM = -7
+};
+
+/* Fusion variants: which reference arithmetic thr_fuse reproduces bit-for-bit. */
+enum {
+  THR_FUSE_RAG2 = 0,   /* w / (k + rank)          src/voice_agent/rag2/retrieval.py:358-376 */
+  THR_FUSE_LIB = 1,    /* w * (1.0 / (k + rank))  triple-hybrid-rag/src/triple_hybrid_rag/core/fusion.py:167-185 */
+  THR_FUSE_RAG1 = 2    /* 1.0 / (k + rank0 + 1)   src/voice_agent/retrieval/hybrid_search.py:460-501 */
+};
+
+/* Order of candidates whose fused fp64 scores are exactly equal. */
+enum {
+  THR_TIE_INSERTION = 0, /* reference behaviour: stable sort, lexical -> semantic -> graph first-seen order */
+  THR_TIE_CHUNK_ID = 1   /* BASELINE.json north_star: ascending chunk id */
+};
+
+typedef struct thr_handle thr_handle;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+
+int thr_abi_version(void);
+int thr_create(int device, thr_handle** out);
+int thr_destroy(thr_handle* h);
+/* Message of the last failure on `h` (h == NULL: last thr_create failure). Never NULL. */
+const char* thr_last_error(const thr_handle* h);
+/* Synchronise `stream` and surface device-side failures recorded since the last thr_sync. */
+int thr_sync(thr_handle* h, void* stream);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t thr_launch_count(const thr_handle* h);
+
+/* ---- K1: semantic channel — exact dense top-k ------------------------------------
+ * Replaces RAG2Retriever._semantic_search -> RPC rag2_semantic_search
+ *   src/voice_agent/rag2/retrieval.py:294-314
+ *   database/migrations/20260114_rag2_schema.sql:377-410   (ORDER BY embedding <=> q LIMIT n;
+ *   similarity = 1 - cosine distance; vectors are L2-normalised so ranking is by dot product).
+ * Exact (brute force), not HNSW.
+ *
+ * X: bf16 [N, D] row-major, resident for the lifetime of the index (not copied).
+ * D must be a multiple of 64, 64 <= D <= 8192.  id_base is added to every returned id
+ * (the shard's first global chunk id).
+ */
+int thr_dense_index_set(thr_handle* h, const void* X, int64_t N, int D, int64_t id_base);
+
+/* Q: bf16 [B, D].  For each query: the k chunks with the largest dot product, ordered by
+ * (score desc, id asc).  Scores are the fp64 dot products of the bf16 inputs (tensor-core
+ * fp32 scores select k + margin survivors, which are re-scored exactly before the final sort).
+ *   out_ids    [B, k] int64   (id_base + row; -1 past out_count)
+ *   out_scores [B, k] double
+ *   out_count  [B]    int32   min(k, N)
+ *   out_gap    [B]    float, nullable: (exact k-th score) - (best tensor-core score that was
+ *              NOT re-scored); the result is certified exact when gap > the fp32 accumulation
+ *              error bound.  +inf when every chunk was re-scored.
+ * 1 <= k, k + margin <= 256.
+ */
+int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin,
+                   int64_t* out_ids, double* out_scores, int32_t* out_count, float* out_gap,
+                   void* stream);
+
+/* ---- K2: lexical channel — BM25 top-k over a blocked CSR inverted index ----------
+ * Replaces RAG2Retriever._lexical_search -> RPC rag2_lexical_search
+ *   src/voice_agent/rag2/retrieval.py:273-292
+ *   database/migrations/20260114_rag2_schema.sql:341-374
+ * (interface: space-joined keywords, top-`limit` by descending score).  The scoring
+ * formula is BM25 as BASELINE.json's north_star asks (Postgres ts_rank_cd is not in the
+ * reference tree); it is defined in oracle/bm25.py and DESIGN.md.
+ *
+ * Index layout (built by triple_hybrid_rag_b200.index.BM25Index on the device):
+ *   documents are split into n_blk ranges of blk_docs consecutive local doc ids;
+ *   postings are ordered by (range, term, doc) and stored as 8-byte records
+ *   {uint32 local_doc, float impact}, impact = tf*(k1+1)/(tf + k1*(1-b+b*len/avgdl));
+ *   blk_ptr [n_blk*(V+1)] int64: postings[blk_ptr[r*(V+1)+t] .. blk_ptr[r*(V+1)+t+1])
+ *   are term t's postings inside range r;  idf [V] float.
+ * blk_docs must be a multiple of 1024 and <= 16384.  Arrays stay resident (not copied).
+ */
+int thr_bm25_index_set(thr_handle* h, const int64_t* blk_ptr, const void* postings,
+                       const float* idf, int64_t n_docs, int32_t n_blk, int32_t blk_docs,
+                       int32_t V, int64_t id_base);
+
+/* q_terms [q_off[B]] int32 term ids (OR semantics; a term id outside [0,V) is ignored),
+ * q_off [B+1] int32.  score(d) = sum over the query's terms IN ORDER of idf[t]*impact(t,d),
+ * accumulated in fp32 (round-to-nearest, no FMA contraction) — the order is part of the
+ * definition, so results are bit-reproducible.  Only docs with score > 0 are eligible;
+ * order is (score desc, id asc).
+ *   out_ids [B,k] int64 (-1 past count), out_scores [B,k] float, out_count [B] int32.
+ * 1 <= k <= 256, at most 32 terms per query.
+ */
+int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                  int64_t* out_ids, float* out_scores, int32_t* out_count, void* stream);
+
+/* ---- K3: weighted RRF fusion + safety threshold + conformal denoise ---------------
+ * Replaces, bit-exactly in fp64:
+ *   THR_FUSE_RAG2: RAG2Retriever._retrieve_candidates merge + _fuse_rrf
+ *                  src/voice_agent/rag2/retrieval.py:203-271, :358-376
+ *   THR_FUSE_LIB : RRFFusion.fuse incl. _apply_safety_threshold, _apply_conformal_denoising
+ *                  triple-hybrid-rag/src/triple_hybrid_rag/core/fusion.py:52-247
+ *   THR_FUSE_RAG1: HybridSearcher._rrf_fusion  src/voice_agent/retrieval/hybrid_search.py:460-501
+ *
+ * Three ranked id lists per query in CSR form (ids int64, off int32 [B+1]); rank = 1 + position.
+ * A NULL ids pointer means the channel is absent for every query.  *_sc are the channels' raw
+ * scores (double, nullable; only THR_FUSE_LIB reads them).  weights [B,3] double in the order
+ * lexical, semantic, graph.  Each list may be at most 256 long.
+ *
+ * THR_FUSE_LIB applies, after the sort: keep rows whose max raw channel score >= safety_thr
+ * (skipped when safety_thr <= 0), then if denoise != 0 and >= 3 rows remain keep rrf >=
+ * numpy.percentile(rrf, (1 - alpha) * 100) (linear interpolation), then truncate to top_k
+ * (top_k <= 0: no truncation).  The other variants only sort and truncate.
+ *
+ * Outputs, row-major with row stride max_out (>= the largest possible union, or >= top_k):
+ *   out_ids [B,max_out] int64, out_rrf [B,max_out] double,
+ *   out_ranks [B,max_out,3] int32 (0 = absent from that channel),
+ *   out_raw [B,max_out,3] double, nullable (merged raw scores, THR_FUSE_LIB),
+ *   out_count [B] int32.
+ */
+int thr_fuse(thr_handle* h, int variant, int tie_mode, int B,
+             const int64_t* lex_ids, const int32_t* lex_off, const double* lex_sc,
+             const int64_t* sem_ids, const int32_t* sem_off, const double* sem_sc,
+             const int64_t* gr_ids, const int32_t* gr_off, const double* gr_sc,
+             const double* weights, int rrf_k, double safety_thr, double alpha, int denoise,
+             int top_k, int max_out,
+             int64_t* out_ids, double* out_rrf, int32_t* out_ranks, double* out_raw,
+             int32_t* out_count, void* stream);
+
+/* RAG2Retriever._apply_safety   src/voice_agent/rag2/retrieval.py:461-495
+ * Per query q with candidates [off[q], off[q+1]) in their current (post-rerank) order:
+ *   s_i = has_rerank[i] && rerank[i] != 0 ? rerank[i] : rrf[i]      (`rerank_score or rrf_score`)
+ *   max_score = max s_i; refused = max_score < threshold  (empty list: refused, max 0)
+ *   keep[i] = !refused && s_i >= alpha*max_score && (#kept before i) < top_k
+ * has_rerank nullable (= all zero).  Outputs keep [n] uint8, refused [B] uint8, max_score [B] double.
+ */
+int thr_safety(thr_handle* h, int B, const int32_t* off, const double* rerank,
+               const uint8_t* has_rerank, const double* rrf, double threshold, double alpha,
+               int top_k, uint8_t* keep, uint8_t* refused, double* max_score, void* stream);
+
+/* ---- K4: late-interaction MaxSim rerank -----------------------------------------
+ * Stands where RAG2Retriever._rerank calls Qwen3VLReranker._rerank_batch_native(query,
+ * documents) -> List[float]   src/voice_agent/rag2/retrieval.py:405-459,
+ * src/voice_agent/retrieval/reranker.py:287-354  (one score per candidate, input order).
+ * score(q, c) = sum_i max_j <Qtok[q,i,:], Dtok[c,j,:]>  over i < q_len[q], j < d_len[c].
+ *
+ * Qtok bf16 [B, Tq, d]; Dtok bf16 [n_docs, Td, d] token store; cand [B, C] int64 rows of
+ * the store (< 0: slot skipped, score -inf); q_len [B] / d_len [n_docs] int32 nullable
+ * (= full).  out [B, C] float.  d == 128, Td in {64,128}, 1 <= Tq <= 128.
+ */
+int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int Tq, int d,
+               const void* Dtok, const int32_t* d_len, int64_t n_docs, int Td,
+               const int64_t* cand, int C, float* out, void* stream);
+
+/* ---- K5: merge of per-shard top-k lists (consumes the all-gather buffer) ----------
+ * scores [G,B,k_in] double, ids [G,B,k_in] int64, counts [G,B] int32 (valid prefix per list).
+ * Per query the k_out best by (score desc, id asc).  G*k_in <= 2048, k_out <= 256.
+ */
+int thr_merge_topk(thr_handle* h, const double* scores, const int64_t* ids,
+                   const int32_t* counts, int G, int B, int k_in, int k_out,
+                   double* out_scores, int64_t* out_ids, int32_t* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THR_H_ */

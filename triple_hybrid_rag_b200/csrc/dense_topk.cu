@@ -1,0 +1,569 @@
+// dense_topk.cu — K1: exact dense top-k (semantic channel).
+//
+// Replaces RAG2Retriever._semantic_search -> rag2_semantic_search
+//   (src/voice_agent/rag2/retrieval.py:294-314, database/migrations/20260114_rag2_schema.sql:377-410):
+//   ORDER BY embedding <=> q LIMIT n on L2-normalised vectors == top-n by dot product.
+//
+// Two kernels:
+//   dense_score_kernel   persistent, warp-specialised tcgen05 GEMM  S = Q . X^T  (bf16 -> fp32 in
+//                        TMEM) whose epilogue never writes S: each TMEM lane (= one query) filters its
+//                        256 fresh scores against a running per-query threshold and appends survivors
+//                        to a small per-(cluster, query) candidate list; lists are compacted to the
+//                        best K' = k + margin by a warp-cooperative radix descent when they fill up.
+//   dense_finalize_kernel one CTA per query: radix-select the global best K' of the cluster lists,
+//                        re-score them exactly (fp64 dot of the bf16 inputs), sort by
+//                        (score desc, id asc), emit top-k and the exactness certificate gap.
+//
+// Layout per cluster step ("tile"): 128*kCtaGroup queries x 256 chunks x D.
+//   kCtaGroup = 2 : CTA pair, tcgen05.mma.cta_group::2 M=256 N=256, each CTA loads 128 query rows and
+//                   128 chunk rows per 64-wide k-block (32 KB / stage / CTA, 6 stages).
+//   kCtaGroup = 1 : single CTA, M=128 N=256 (48 KB / stage, 4 stages) — fallback and bring-up path.
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
+// warp 5 TMEM allocator + MMA issuer.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;       // query rows per CTA
+constexpr int kTileN = 256;        // chunks per tile (UMMA N)
+constexpr int kBlockK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kAccStages = 2;      // 2 x 256 TMEM columns
+constexpr int kTmemCols = 512;
+constexpr int kCap = 512;          // candidate slots per (cluster, query)
+constexpr int kMaxSel = 256;       // largest K' = k + margin
+constexpr int kScoreThreads = 192;
+constexpr int kFinalThreads = 256;
+
+template <int G> struct ScoreCfg {
+  static constexpr int kStages = (G == 2) ? 6 : 4;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;                 // 16 KB
+  static constexpr int kBBytes = (G == 2 ? 128 : 256) * kBlockK * 2;    // 16 / 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTxBytes = kStageBytes * G;                      // per full barrier phase
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct ScoreArgs {
+  int B;            // queries
+  int64_t N;        // chunks
+  int D;
+  int ksel;         // K' = k + margin
+  int n_clusters;
+  int Bpad;         // row stride of cand/cnt
+  uint64_t* cand;   // [n_clusters][Bpad][kCap]
+  int32_t* cnt;     // [n_clusters][Bpad]
+  thr_dev_status* status;
+};
+
+// Warp-cooperative: keep the `ksel` largest of the n (<= kCap) distinct keys in row[0..n), in place.
+// Returns the ksel-th largest key (valid in every lane).  Requires n > ksel.
+__device__ uint64_t warp_compact_topk(uint64_t* row, int n, int ksel, uint32_t lane) {
+  constexpr int kPer = kCap / 32;
+  uint32_t hi[kPer], lo[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    int i = lane + 32 * j;
+    uint64_t key = i < n ? row[i] : 0ull;
+    hi[j] = (uint32_t)(key >> 32);
+    lo[j] = (uint32_t)key;
+  }
+  // radix descent over the 64 key bits: T = largest value with count(keys >= T) >= ksel
+  uint32_t t_hi = 0, t_lo = 0;
+  bool exact = false;
+  for (int bit = 31; bit >= 0 && !exact; --bit) {
+    uint32_t c_hi = t_hi | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) c += (hi[j] >= c_hi) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= ksel) t_hi = c_hi;
+    exact = (c == ksel);
+  }
+  for (int bit = 31; bit >= 0 && !exact; --bit) {
+    uint32_t c_lo = t_lo | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) c += (hi[j] > t_hi || (hi[j] == t_hi && lo[j] >= c_lo)) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= ksel) t_lo = c_lo;
+    exact = (c == ksel);
+  }
+  // compact survivors to the front (order is irrelevant) and find the smallest survivor
+  __syncwarp();
+  int base = 0;
+  uint32_t m_hi = 0xffffffffu, m_lo = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    bool keep = hi[j] > t_hi || (hi[j] == t_hi && lo[j] >= t_lo);
+    keep = keep && (int)(lane + 32 * j) < n;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      row[base + __popc(bal & ((1u << lane) - 1))] = ((uint64_t)hi[j] << 32) | lo[j];
+      if (hi[j] < m_hi || (hi[j] == m_hi && lo[j] < m_lo)) { m_hi = hi[j]; m_lo = lo[j]; }
+    }
+    base += __popc(bal);
+  }
+  uint64_t mn = ((uint64_t)m_hi << 32) | m_lo;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    uint64_t o = __shfl_xor_sync(0xffffffffu, mn, s);
+    mn = o < mn ? o : mn;
+  }
+  __syncwarp();
+  return mn;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kScoreThreads, 1)
+dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                   const ScoreArgs a) {
+  using Cfg = ScoreCfg<G>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: SWIZZLE_128B atoms and UMMA descriptors with base_offset = 0
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + kAccStages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 2 * kAccStages);
+  auto a_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto b_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = (G == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = (G == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const bool leader = rank == 0;
+
+  const int kblocks = a.D / kBlockK;
+  const int64_t tiles_total = (a.N + kTileN - 1) / kTileN;
+  const int64_t tile_lo = tiles_total * cluster_id / a.n_clusters;
+  const int64_t tile_hi = tiles_total * (cluster_id + 1) / a.n_clusters;
+  const int qrows = kBlockM * G;
+  const int qblocks = (a.B + qrows - 1) / qrows;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4 * G);
+    }
+    fence_mbar_init_cluster();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_x);
+  }
+  if (warp == 5) {
+    tmem_alloc<G>(tmem_slot, kTmemCols);
+    tmem_relinquish<G>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (G == 2) cluster_sync_all();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    // ===================== TMA producer (one lane, both CTAs of a pair) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      bool ok = true;
+      for (int qb = 0; qb < qblocks && ok; ++qb) {
+        const int q_row = qb * qrows + (int)rank * kBlockM;
+        for (int64_t t = tile_lo; t < tile_hi && ok; ++t) {
+          const int64_t x_row = t * kTileN + (G == 2 ? (int64_t)rank * 128 : 0);
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1u;
+            if (!mbar_wait(empty_bar(s), ph ^ 1u, a.status, 100)) { ok = false; break; }
+            const uint32_t fb = (G == 2) ? mapa_u32(full_bar(s), 0) : full_bar(s);
+            if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::kTxBytes);
+            if (G == 2) {
+              tma_load_2d_pair(a_smem(s), &map_q, fb, kb * kBlockK, q_row, THR_L2_EVICT_LAST);
+              tma_load_2d_pair(b_smem(s), &map_x, fb, kb * kBlockK, (int32_t)x_row, THR_L2_EVICT_FIRST);
+            } else {
+              tma_load_2d(a_smem(s), &map_q, fb, kb * kBlockK, q_row, THR_L2_EVICT_LAST);
+              tma_load_2d(b_smem(s), &map_x, fb, kb * kBlockK, (int32_t)x_row, THR_L2_EVICT_FIRST);
+              tma_load_2d(b_smem(s) + 128 * kBlockK * 2, &map_x, fb, kb * kBlockK,
+                          (int32_t)x_row + 128, THR_L2_EVICT_FIRST);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer (leader CTA, one lane) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM * G, kTileN);
+      uint32_t it = 0, tcount = 0;
+      bool ok = true;
+      for (int qb = 0; qb < qblocks && ok; ++qb) {
+        for (int64_t t = tile_lo; t < tile_hi && ok; ++t, ++tcount) {
+          const int acc = tcount & 1;
+          const uint32_t aph = (tcount >> 1) & 1u;
+          if (!mbar_wait_cluster(tempty_bar(acc), aph ^ 1u, a.status, 200)) { ok = false; break; }
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1u;
+            if (!mbar_wait(full_bar(s), ph, a.status, 201)) { ok = false; break; }
+            tc_fence_after_sync();
+            const uint64_t adesc = umma_desc_sw128(a_smem(s));
+            const uint64_t bdesc = umma_desc_sw128(b_smem(s));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle row (>>4 in the address field)
+              umma_bf16<G>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            }
+            if (G == 2) umma_commit_pair_mcast(empty_bar(s), 0x3);
+            else umma_commit_1cta(empty_bar(s));
+          }
+          if (!ok) break;
+          if (G == 2) umma_commit_pair_mcast(tfull_bar(acc), 0x3);
+          else umma_commit_1cta(tfull_bar(acc));
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: fused per-query top-K' filter =====================
+    const uint32_t lane_base = warp * 32;  // TMEM lane quarter of this warp
+    uint32_t tcount = 0;
+    bool ok = true;
+    for (int qb = 0; qb < qblocks && ok; ++qb) {
+      const int row = qb * qrows + (int)rank * kBlockM + (int)lane_base + (int)lane;  // query index
+      const bool row_valid = row < a.B;
+      uint64_t* rowbuf = a.cand + ((size_t)cluster_id * a.Bpad + (row_valid ? row : 0)) * kCap;
+      float tau = -CUDART_INF_F;
+      int cnt = 0;
+      for (int64_t t = tile_lo; t < tile_hi && ok; ++t, ++tcount) {
+        const int acc = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1u;
+        // make room: a tile can add up to kTileN survivors per query
+        unsigned need = __ballot_sync(0xffffffffu, row_valid && cnt > kCap - kTileN);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+          uint64_t* buf_src = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)rowbuf, src);
+          __syncwarp();
+          const uint64_t kth = warp_compact_topk(buf_src, n_src, a.ksel, lane);
+          if ((int)lane == src) { cnt = a.ksel; tau = key_score(kth); }
+        }
+        // warp-uniform outcome: the loop below uses full-mask warp collectives
+        if (!__all_sync(0xffffffffu, mbar_wait(tfull_bar(acc), aph, a.status, 300))) { ok = false; break; }
+        tc_fence_after_sync();
+        const int64_t col0 = t * kTileN;
+        const int ncols = (int)min((int64_t)kTileN, a.N - col0);
+#pragma unroll 1
+        for (int c = 0; c < kTileN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (lane_base << 16) + (uint32_t)(acc * kTileN + c * 32), r);
+          tmem_ld_wait();
+          if (row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              const int col = c * 32 + j;
+              if (v > tau && col < ncols) {
+                if (cnt < kCap) rowbuf[cnt] = pack_key(v, (uint32_t)(col0 + col));
+                ++cnt;
+              }
+            }
+          }
+        }
+        if (cnt > kCap) {  // cannot happen given the pre-tile compaction; keep the invariant loud
+          dev_report(a.status, THR_EOVERFLOW, 301, cnt);
+          cnt = kCap;
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (G == 2) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));
+          else mbar_arrive(tempty_bar(acc));
+        }
+      }
+      // final compaction of this query block: every list ends with <= K' entries
+      unsigned need = __ballot_sync(0xffffffffu, row_valid && cnt > a.ksel);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+        uint64_t* buf_src = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)rowbuf, src);
+        __syncwarp();
+        (void)warp_compact_topk(buf_src, n_src, a.ksel, lane);
+        if ((int)lane == src) cnt = a.ksel;
+      }
+      if (row_valid) a.cnt[(size_t)cluster_id * a.Bpad + row] = ok ? cnt : 0;
+    }
+  }
+
+  // ---- teardown: nobody may exit (or free TMEM) while the peer can still signal us ----
+  tc_fence_before_sync();
+  __syncthreads();
+  if (G == 2) cluster_sync_all();
+  if (warp == 5) {
+    __syncwarp();
+    tmem_dealloc<G>(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finalize: global select + exact re-score + sort.
+// ------------------------------------------------------------------------------------------------
+struct FinalArgs {
+  const __nv_bfloat16* Q;
+  const __nv_bfloat16* X;
+  int B, D;
+  int64_t N, id_base;
+  int k, ksel, n_clusters, Bpad;
+  const uint64_t* cand;
+  const int32_t* cnt;
+  int64_t* out_ids;
+  double* out_scores;
+  int32_t* out_count;
+  float* out_gap;
+};
+
+__global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const FinalArgs a) {
+  extern __shared__ uint8_t fsm[];
+  // layout: keys [n_clusters*ksel] u64 | qrow [D] bf16
+  uint64_t* keys = (uint64_t*)fsm;
+  __nv_bfloat16* qrow = (__nv_bfloat16*)(keys + (size_t)a.n_clusters * a.ksel);
+  __shared__ uint32_t hist[256];
+  __shared__ uint64_t s_prefix;
+  __shared__ int s_want, s_m, s_nsel;
+  __shared__ uint64_t sel_key[kMaxSel];
+  __shared__ double sel_score[kMaxSel];
+  __shared__ uint32_t sel_idx[kMaxSel];
+
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_m = 0; s_nsel = 0; }
+  for (int i = tid; i < a.D; i += kFinalThreads) qrow[i] = a.Q[(size_t)q * a.D + i];
+  __syncthreads();
+
+  // 1. gather the per-cluster lists of this query
+  for (int c = warp; c < a.n_clusters; c += kFinalThreads / 32) {
+    const int n = min(a.cnt[(size_t)c * a.Bpad + q], a.ksel);
+    const uint64_t* src = a.cand + ((size_t)c * a.Bpad + q) * kCap;
+    int base = 0;
+    if (lane == 0 && n > 0) base = atomicAdd(&s_m, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < n; i += 32) keys[base + i] = src[i];
+  }
+  __syncthreads();
+  const int m = s_m;
+  const int nsel = min(m, a.ksel);
+
+  // 2. K'-th largest key by MSD radix select (8 bits per pass); keys are distinct
+  uint64_t T = 0;
+  if (m > a.ksel) {
+    if (tid == 0) { s_prefix = 0; s_want = a.ksel; }
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      hist[tid] = 0;
+      __syncthreads();
+      const uint64_t prefix = s_prefix;
+      for (int i = tid; i < m; i += kFinalThreads) {
+        const uint64_t key = keys[i];
+        const bool match = pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8));
+        if (match) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int want = s_want, cum = 0, d = 255;
+        for (; d > 0; --d) {
+          if (cum + (int)hist[d] >= want) break;
+          cum += hist[d];
+        }
+        s_want = want - cum;
+        s_prefix = prefix | ((uint64_t)d << shift);
+      }
+      __syncthreads();
+    }
+    T = s_prefix;
+  }
+
+  // 3. collect survivors
+  for (int i = tid; i < m; i += kFinalThreads) {
+    const uint64_t key = keys[i];
+    if (key >= T) {
+      int slot = atomicAdd(&s_nsel, 1);
+      if (slot < kMaxSel) sel_key[slot] = key;
+    }
+  }
+  __syncthreads();
+
+  // 4. exact re-score: fp64 dot of the bf16 inputs, one warp per survivor, fixed summation order
+  for (int i = warp; i < nsel; i += kFinalThreads / 32) {
+    const uint32_t idx = key_index(sel_key[i]);
+    const __nv_bfloat16* x = a.X + (size_t)idx * a.D;
+    double acc = 0.0;
+    for (int d0 = lane * 8; d0 < a.D; d0 += 256) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(x + d0);
+      const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        acc = fma((double)__bfloat162float(xe[e]), (double)__bfloat162float(qrow[d0 + e]), acc);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) { sel_score[i] = acc; sel_idx[i] = idx; }
+  }
+  for (int i = nsel + tid; i < kMaxSel; i += kFinalThreads) { sel_score[i] = -CUDART_INF; sel_idx[i] = 0xffffffffu; }
+  __syncthreads();
+
+  // 5. bitonic sort of 256 slots by (score desc, idx asc); one slot per thread
+  for (int size = 2; size <= kMaxSel; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < kMaxSel / 2) {
+        int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
+        int hi = lo + stride;
+        bool ascending = ((lo & size) == 0);
+        double sl = sel_score[lo], sh = sel_score[hi];
+        uint32_t il = sel_idx[lo], ih = sel_idx[hi];
+        bool hi_before_lo = (sh > sl) || (sh == sl && ih < il);
+        bool lo_before_hi = (sl > sh) || (sl == sh && il < ih);
+        bool swap = ascending ? hi_before_lo : lo_before_hi;
+        if (swap) { sel_score[lo] = sh; sel_score[hi] = sl; sel_idx[lo] = ih; sel_idx[hi] = il; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // 6. outputs
+  const int nout = min(nsel, a.k);
+  if (tid == 0) {
+    a.out_count[q] = nout;
+    if (a.out_gap) {
+      // every chunk that was not re-scored has a tensor-core score <= score(T)
+      float gap = CUDART_INF_F;
+      if (m > a.ksel && nout > 0) gap = (float)(sel_score[nout - 1] - (double)key_score(T));
+      a.out_gap[q] = gap;
+    }
+  }
+  for (int i = tid; i < a.k; i += kFinalThreads) {
+    size_t o = (size_t)q * a.k + i;
+    a.out_ids[o] = i < nout ? a.id_base + (int64_t)sel_idx[i] : -1;
+    a.out_scores[o] = i < nout ? sel_score[i] : -CUDART_INF;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+struct thr_dense_state {
+  const void* X;
+  int64_t N;
+  int D;
+  int64_t id_base;
+  CUtensorMap map_x;
+  int cta_group;  // 2 (pair) or 1; THR_DENSE_CTA_GROUP overrides for bring-up
+};
+
+void thr_dense_state_free(thr_handle* h) {
+  if (h->dense) { free(h->dense); h->dense = nullptr; }
+}
+
+template <int G>
+static int launch_score(thr_handle* h, const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a,
+                        cudaStream_t stream) {
+  using Cfg = ScoreCfg<G>;
+  THR_CUDA(h, cudaFuncSetAttribute(dense_score_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.n_clusters * G);
+  cfg.blockDim = dim3(kScoreThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  THR_CUDA(h, cudaLaunchKernelEx(&cfg, dense_score_kernel<G>, mq, mx, a));
+  h->launches++;
+  return THR_OK;
+}
+
+extern "C" {
+
+int thr_dense_index_set(thr_handle* h, const void* X, int64_t N, int D, int64_t id_base) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, X != nullptr && N >= 1, "thr_dense_index_set: empty index");
+  THR_REQUIRE(h, N < (int64_t)1 << 31, "thr_dense_index_set: N = %lld exceeds 2^31 rows per shard", (long long)N);
+  if (D % kBlockK != 0 || D < kBlockK || D > 8192)
+    return thr_fail(h, THR_EUNSUPPORTED, "thr_dense_index_set: D = %d must be a multiple of 64 in [64, 8192]", D);
+  thr_dense_state_free(h);
+  thr_dense_state* st = (thr_dense_state*)calloc(1, sizeof(thr_dense_state));
+  if (!st) return thr_fail(h, THR_ENOMEM, "out of host memory");
+  st->X = X; st->N = N; st->D = D; st->id_base = id_base;
+  int rc = thr_encode_tma_2d_bf16(h, &st->map_x, X, (uint64_t)N, (uint64_t)D, 128, kBlockK);
+  if (rc != THR_OK) { free(st); return rc; }
+  st->cta_group = 2;
+  const char* env = getenv("THR_DENSE_CTA_GROUP");
+  if (env && env[0] == '1') st->cta_group = 1;
+  h->dense = st;
+  return THR_OK;
+}
+
+int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64_t* out_ids,
+                   double* out_scores, int32_t* out_count, float* out_gap, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  thr_dense_state* st = h->dense;
+  if (!st) return thr_fail(h, THR_ENOINDEX, "thr_dense_topk: call thr_dense_index_set first");
+  THR_REQUIRE(h, B >= 0 && k >= 1 && margin >= 0, "thr_dense_topk: bad B/k/margin");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, k + margin <= kMaxSel, "thr_dense_topk: k + margin = %d exceeds %d", k + margin, kMaxSel);
+  THR_REQUIRE(h, Q && out_ids && out_scores && out_count, "thr_dense_topk: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int G = st->cta_group;
+  const int64_t tiles = (st->N + kTileN - 1) / kTileN;
+  int n_clusters = h->num_sms / G;
+  if ((int64_t)n_clusters > tiles) n_clusters = (int)tiles;
+  const int Bpad = (B + 255) & ~255;
+  const size_t cand_bytes = (size_t)n_clusters * Bpad * kCap * sizeof(uint64_t);
+  const size_t cnt_bytes = (size_t)n_clusters * Bpad * sizeof(int32_t);
+  uint8_t* ws = (uint8_t*)thr_scratch(h, cand_bytes + cnt_bytes);
+  if (!ws) return THR_ENOMEM;
+
+  CUtensorMap map_q;
+  int rc = thr_encode_tma_2d_bf16(h, &map_q, Q, (uint64_t)B, (uint64_t)st->D, 128, kBlockK);
+  if (rc != THR_OK) return rc;
+
+  ScoreArgs a;
+  a.B = B; a.N = st->N; a.D = st->D; a.ksel = k + margin; a.n_clusters = n_clusters; a.Bpad = Bpad;
+  a.cand = (uint64_t*)ws; a.cnt = (int32_t*)(ws + cand_bytes); a.status = h->d_status;
+  THR_CUDA(h, cudaMemsetAsync(a.cnt, 0, cnt_bytes, s));
+  rc = (G == 2) ? launch_score<2>(h, map_q, st->map_x, a, s) : launch_score<1>(h, map_q, st->map_x, a, s);
+  if (rc != THR_OK) return rc;
+
+  FinalArgs f;
+  f.Q = (const __nv_bfloat16*)Q; f.X = (const __nv_bfloat16*)st->X; f.B = B; f.D = st->D; f.N = st->N;
+  f.id_base = st->id_base; f.k = k; f.ksel = k + margin; f.n_clusters = n_clusters; f.Bpad = Bpad;
+  f.cand = a.cand; f.cnt = a.cnt; f.out_ids = out_ids; f.out_scores = out_scores;
+  f.out_count = out_count; f.out_gap = out_gap;
+  const size_t fsmem = (size_t)n_clusters * f.ksel * sizeof(uint64_t) + (size_t)st->D * 2;
+  THR_CUDA(h, cudaFuncSetAttribute(dense_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  dense_finalize_kernel<<<B, kFinalThreads, fsmem, s>>>(f);
+  THR_CHECK_LAUNCH(h, "dense_finalize_kernel");
+  return THR_OK;
+}
+
+}  // extern "C"

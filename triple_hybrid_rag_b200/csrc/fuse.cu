@@ -1,0 +1,447 @@
+// fuse.cu — K3: weighted RRF fusion + safety threshold + conformal denoise, K5: shard merge,
+// and the RAG 2.0 safety/denoise filter.  All arithmetic that the reference does in Python
+// floats is done here in fp64 with explicit round-to-nearest intrinsics (no FMA contraction),
+// in the reference's operation order, so results are bit-identical.
+//
+// Reference semantics restated (paths relative to the reference checkout):
+//   merge + ranks : src/voice_agent/rag2/retrieval.py:203-271
+//   RRF (RAG2)    : src/voice_agent/rag2/retrieval.py:358-376          w / (k + rank)
+//   RRF (library) : triple-hybrid-rag/src/triple_hybrid_rag/core/fusion.py:52-185   w * (1.0 / (k + rank))
+//   RRF (RAG1)    : src/voice_agent/retrieval/hybrid_search.py:460-501 1.0 / (k + rank0 + 1)
+//   safety (lib)  : fusion.py:187-216, denoise: fusion.py:218-247 (numpy.percentile, linear)
+//   safety (RAG2) : src/voice_agent/rag2/retrieval.py:461-495
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxList = 256;            // longest single channel list
+constexpr int kMaxEntries = 3 * kMaxList;
+constexpr int kSortPad = 1024;
+constexpr int kFuseThreads = 256;
+
+struct FuseArgs {
+  const int64_t* ids[3];
+  const int32_t* off[3];
+  const double* sc[3];
+  const double* weights;  // [B,3]
+  int rrf_k;
+  double safety_thr;
+  double alpha;
+  int denoise;
+  int top_k;
+  int max_out;
+  int tie_mode;
+  int64_t* out_ids;
+  double* out_rrf;
+  int32_t* out_ranks;
+  double* out_raw;
+  int32_t* out_count;
+  thr_dev_status* status;
+};
+
+// numpy.percentile(a, q) with method="linear" (numpy 2.x, lib/_function_base_impl.py:
+// _QuantileMethods['linear'], _get_indexes, _get_gamma, _lerp) on an ascending array that is
+// given as the reverse of `desc` (a[i] = desc[n-1-i]).
+__device__ double percentile_linear_desc(const double* desc_vals, const uint16_t* order, int n,
+                                         double q) {
+  double quant = __ddiv_rn(q, 100.0);
+  double vi = __dmul_rn((double)(n - 1), quant);
+  long long lo, hi;
+  if (vi >= (double)(n - 1)) {
+    lo = hi = n - 1;
+  } else if (vi < 0.0) {
+    lo = hi = 0;
+  } else {
+    lo = (long long)floor(vi);
+    hi = lo + 1;
+  }
+  // gamma uses the (possibly clamped) previous index exactly as numpy does; when lo == hi the
+  // interpolation collapses to a[lo] for finite inputs.
+  double prev_for_gamma = (vi >= (double)(n - 1)) ? -1.0 : ((vi < 0.0) ? 0.0 : (double)lo);
+  double t = __dsub_rn(vi, prev_for_gamma);
+  double a = desc_vals[order[n - 1 - lo]];
+  double b = desc_vals[order[n - 1 - hi]];
+  double diff = __dsub_rn(b, a);
+  double r = __dadd_rn(a, __dmul_rn(diff, t));
+  if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+  return r;
+}
+
+template <int kVariant>
+__global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
+  __shared__ int64_t e_id[kMaxEntries];
+  __shared__ double e_rrf[kMaxEntries];
+  __shared__ double e_raw[3][kMaxEntries];
+  __shared__ uint16_t e_rank[3][kMaxEntries];
+  __shared__ uint16_t e_pos[kMaxEntries];
+  __shared__ uint8_t e_chan[kMaxEntries];
+  __shared__ uint16_t perm[kSortPad];
+  __shared__ uint8_t keep[kMaxEntries];
+  __shared__ int s_n[4];      // entries per channel + total
+  __shared__ int s_unique;
+  __shared__ double s_thr;
+  __shared__ int s_out;
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    int tot = 0;
+    for (int c = 0; c < 3; ++c) {
+      int n = 0;
+      if (a.ids[c] != nullptr) n = a.off[c][q + 1] - a.off[c][q];
+      if (n > kMaxList) {
+        dev_report(a.status, THR_EOVERFLOW, 300 + c, n);
+        n = kMaxList;
+      }
+      s_n[c] = n;
+      tot += n;
+    }
+    s_n[3] = tot;
+    s_unique = 0;
+  }
+  __syncthreads();
+  const int n0 = s_n[0], n1 = s_n[1], n = s_n[3];
+
+  // 1. concatenate lexical -> semantic -> graph (the reference's dict insertion order)
+  for (int e = tid; e < n; e += kFuseThreads) {
+    int c = e < n0 ? 0 : (e < n0 + n1 ? 1 : 2);
+    int p = e - (c == 0 ? 0 : (c == 1 ? n0 : n0 + n1));
+    int64_t src = (int64_t)a.off[c][q] + p;
+    e_id[e] = a.ids[c][src];
+    e_chan[e] = (uint8_t)c;
+    e_pos[e] = (uint16_t)p;
+    e_raw[c][e] = (kVariant != THR_FUSE_RAG2 && a.sc[c] != nullptr) ? a.sc[c][src] : 0.0;
+  }
+  for (int i = tid; i < kSortPad; i += kFuseThreads) perm[i] = 0xffff;
+  __syncthreads();
+
+  // 2. one candidate per distinct id, owned by its first occurrence
+  const double w[3] = {a.weights[q * 3 + 0], a.weights[q * 3 + 1], a.weights[q * 3 + 2]};
+  for (int e = tid; e < n; e += kFuseThreads) {
+    const int64_t id = e_id[e];
+    bool first = true;
+    for (int j = 0; j < e; ++j)
+      if (e_id[j] == id) { first = false; break; }
+    if (!first) continue;
+
+    int last_rank[3] = {0, 0, 0};  // 1-based rank of the LAST occurrence per channel
+    int occ[3] = {0, 0, 0};
+    double raw[3] = {0.0, 0.0, 0.0};
+    double rrf = 0.0;
+    for (int j = e; j < n; ++j) {
+      if (e_id[j] != id) continue;
+      int c = e_chan[j];
+      int r = (int)e_pos[j] + 1;
+      last_rank[c] = r;
+      occ[c] += 1;
+      if (kVariant == THR_FUSE_LIB) raw[c] = e_raw[c][j];                  // last one wins
+      if (kVariant == THR_FUSE_RAG1) {
+        raw[c] = fmax(raw[c], e_raw[c][j]);                                // best individual score
+        rrf = __dadd_rn(rrf, __ddiv_rn(1.0, (double)(a.rrf_k + r)));       // r = rank0 + 1
+      }
+    }
+    if (kVariant == THR_FUSE_RAG2) {
+      for (int c = 0; c < 3; ++c)
+        if (last_rank[c]) rrf = __dadd_rn(rrf, __ddiv_rn(w[c], (double)(a.rrf_k + last_rank[c])));
+    } else if (kVariant == THR_FUSE_LIB) {
+      for (int c = 0; c < 3; ++c) {
+        if (!occ[c]) continue;
+        double s = __dmul_rn(w[c], __ddiv_rn(1.0, (double)(a.rrf_k + last_rank[c])));
+        for (int k = 0; k < occ[c]; ++k) rrf = __dadd_rn(rrf, s);  // the merge loop adds once per occurrence
+      }
+    }
+    e_rrf[e] = rrf;
+    for (int c = 0; c < 3; ++c) {
+      e_rank[c][e] = (uint16_t)last_rank[c];
+      e_raw[c][e] = raw[c];
+    }
+    int slot = atomicAdd(&s_unique, 1);
+    perm[slot] = (uint16_t)e;
+  }
+  __syncthreads();
+  const int m = s_unique;
+
+  // 3. sort by (rrf desc, tie asc); tie = first-seen index (stable sort) or chunk id
+  int P = 32;
+  while (P < m) P <<= 1;
+  auto before = [&](uint16_t x, uint16_t y) -> bool {  // x strictly before y
+    if (x == 0xffff) return false;
+    if (y == 0xffff) return true;
+    double rx = e_rrf[x], ry = e_rrf[y];
+    if (rx != ry) return rx > ry;
+    if (a.tie_mode == THR_TIE_CHUNK_ID) {
+      int64_t ix = e_id[x], iy = e_id[y];
+      if (ix != iy) return ix < iy;
+    }
+    return x < y;
+  };
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P >> 1); i += kFuseThreads) {
+        int lo = ((i / stride) * (stride << 1)) + (i % stride);
+        int hi = lo + stride;
+        bool ascending = ((lo & size) == 0);
+        uint16_t x = perm[lo], y = perm[hi];
+        bool swap = ascending ? before(y, x) : before(x, y);
+        if (swap) { perm[lo] = y; perm[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // 4. filters (library variant), then truncation
+  for (int i = tid; i < m; i += kFuseThreads) {
+    bool k = true;
+    if (kVariant == THR_FUSE_LIB && a.safety_thr > 0.0) {
+      int e = perm[i];
+      // max(semantic or 0.0, lexical or 0.0, graph or 0.0): Python's max keeps the first of equals
+      double mx = e_raw[1][e];
+      if (e_raw[0][e] > mx) mx = e_raw[0][e];
+      if (e_raw[2][e] > mx) mx = e_raw[2][e];
+      k = mx >= a.safety_thr;
+    }
+    keep[i] = k;
+  }
+  __syncthreads();
+
+  if (tid < 32) {
+    // compact `keep` in order (warp 0), reusing perm in place (write index <= read index)
+    int base = 0;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+      int i = i0 + tid;
+      bool k = i < m && keep[i];
+      uint16_t v = i < m ? perm[i] : 0xffff;
+      unsigned bal = __ballot_sync(0xffffffffu, k);
+      __syncwarp();
+      if (k) perm[base + __popc(bal & ((1u << tid) - 1))] = v;
+      base += __popc(bal);
+      __syncwarp();
+    }
+    int nA = base;
+    if (kVariant == THR_FUSE_LIB && a.denoise && nA >= 3) {
+      if (tid == 0) {
+        double qpct = __dmul_rn(__dsub_rn(1.0, a.alpha), 100.0);
+        s_thr = percentile_linear_desc(e_rrf, perm, nA, qpct);
+      }
+      __syncwarp();
+      double thr = s_thr;
+      int base2 = 0;
+      for (int i0 = 0; i0 < nA; i0 += 32) {
+        int i = i0 + tid;
+        uint16_t v = i < nA ? perm[i] : 0xffff;
+        bool k = i < nA && e_rrf[v] >= thr;
+        unsigned bal = __ballot_sync(0xffffffffu, k);
+        __syncwarp();
+        if (k) perm[base2 + __popc(bal & ((1u << tid) - 1))] = v;
+        base2 += __popc(bal);
+        __syncwarp();
+      }
+      nA = base2;
+    }
+    if (a.top_k > 0 && nA > a.top_k) nA = a.top_k;
+    if (nA > a.max_out) {
+      if (tid == 0) dev_report(a.status, THR_EOVERFLOW, 310, nA);
+      nA = a.max_out;
+    }
+    if (tid == 0) s_out = nA;
+  }
+  __syncthreads();
+
+  // 5. outputs
+  const int nout = s_out;
+  if (tid == 0) a.out_count[q] = nout;
+  for (int i = tid; i < a.max_out; i += kFuseThreads) {
+    size_t o = (size_t)q * a.max_out + i;
+    if (i < nout) {
+      int e = perm[i];
+      a.out_ids[o] = e_id[e];
+      a.out_rrf[o] = e_rrf[e];
+      for (int c = 0; c < 3; ++c) {
+        a.out_ranks[o * 3 + c] = e_rank[c][e];
+        if (a.out_raw) a.out_raw[o * 3 + c] = e_raw[c][e];
+      }
+    } else {
+      a.out_ids[o] = -1;
+      a.out_rrf[o] = 0.0;
+      for (int c = 0; c < 3; ++c) {
+        a.out_ranks[o * 3 + c] = 0;
+        if (a.out_raw) a.out_raw[o * 3 + c] = 0.0;
+      }
+    }
+  }
+}
+
+// RAG2Retriever._apply_safety — one warp per query.
+__global__ void __launch_bounds__(128) safety_kernel(int B, const int32_t* off, const double* rerank,
+                                                     const uint8_t* has_rerank, const double* rrf,
+                                                     double threshold, double alpha, int top_k,
+                                                     uint8_t* keep, uint8_t* refused,
+                                                     double* max_score) {
+  int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (q >= B) return;
+  int lo = off[q], hi = off[q + 1];
+  auto score = [&](int i) -> double {
+    // `c.rerank_score or c.rrf_score`: None and 0.0 are both falsy
+    if (has_rerank && has_rerank[i] && rerank[i] != 0.0) return rerank[i];
+    return rrf[i];
+  };
+  if (hi <= lo) {
+    if (lane == 0) { refused[q] = 1; max_score[q] = 0.0; }
+    return;
+  }
+  double mx = -INFINITY;
+  for (int i = lo + lane; i < hi; i += 32) mx = fmax(mx, score(i));
+  for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  bool ref = mx < threshold;
+  if (lane == 0) { refused[q] = ref ? 1 : 0; max_score[q] = mx; }
+  double min_score = __dmul_rn(alpha, mx);
+  int kept = 0;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    int i = i0 + lane;
+    bool k = !ref && i < hi && score(i) >= min_score;
+    unsigned bal = __ballot_sync(0xffffffffu, k);
+    int before = kept + __popc(bal & ((1u << lane) - 1));
+    if (i < hi) keep[i] = (k && before < top_k) ? 1 : 0;
+    kept += __popc(bal);
+  }
+}
+
+// K5: per query merge of G lists of (score, id) -> k_out best by (score desc, id asc).
+constexpr int kMergeMax = 2048;
+__global__ void __launch_bounds__(256) merge_kernel(const double* scores, const int64_t* ids,
+                                                    const int32_t* counts, int G, int B, int k_in,
+                                                    int k_out, double* out_scores, int64_t* out_ids,
+                                                    int32_t* out_count) {
+  __shared__ double s_sc[kMergeMax];
+  __shared__ int64_t s_id[kMergeMax];
+  __shared__ int s_total;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int n = G * k_in;
+  int P = 32;
+  while (P < n) P <<= 1;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < P; i += 256) {
+    double s = -INFINITY;
+    int64_t id = INT64_MAX;
+    if (i < n) {
+      int g = i / k_in, j = i % k_in;
+      int cnt = counts ? counts[g * B + q] : k_in;
+      if (j < cnt) {
+        size_t src = ((size_t)g * B + q) * k_in + j;
+        s = scores[src];
+        id = ids[src];
+        ++local;
+      }
+    }
+    s_sc[i] = s;
+    s_id[i] = id;
+  }
+  if (local) atomicAdd(&s_total, local);
+  __syncthreads();
+  auto before = [&](int x, int y) -> bool {
+    int64_t ix = s_id[x], iy = s_id[y];
+    bool vx = ix != INT64_MAX, vy = iy != INT64_MAX;
+    if (vx != vy) return vx;
+    double sx = s_sc[x], sy = s_sc[y];
+    if (sx != sy) return sx > sy;
+    return ix < iy;
+  };
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P >> 1); i += 256) {
+        int lo = ((i / stride) * (stride << 1)) + (i % stride);
+        int hi = lo + stride;
+        bool ascending = ((lo & size) == 0);
+        bool swap = ascending ? before(hi, lo) : before(lo, hi);
+        if (swap) {
+          double ts = s_sc[lo]; s_sc[lo] = s_sc[hi]; s_sc[hi] = ts;
+          int64_t ti = s_id[lo]; s_id[lo] = s_id[hi]; s_id[hi] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int nout = min(s_total, k_out);
+  if (tid == 0) out_count[q] = nout;
+  for (int i = tid; i < k_out; i += 256) {
+    size_t o = (size_t)q * k_out + i;
+    out_scores[o] = i < nout ? s_sc[i] : -INFINITY;
+    out_ids[o] = i < nout ? s_id[i] : -1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int thr_fuse(thr_handle* h, int variant, int tie_mode, int B, const int64_t* lex_ids,
+             const int32_t* lex_off, const double* lex_sc, const int64_t* sem_ids,
+             const int32_t* sem_off, const double* sem_sc, const int64_t* gr_ids,
+             const int32_t* gr_off, const double* gr_sc, const double* weights, int rrf_k,
+             double safety_thr, double alpha, int denoise, int top_k, int max_out,
+             int64_t* out_ids, double* out_rrf, int32_t* out_ranks, double* out_raw,
+             int32_t* out_count, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, B >= 0, "thr_fuse: B < 0");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, variant >= THR_FUSE_RAG2 && variant <= THR_FUSE_RAG1, "thr_fuse: unknown variant %d", variant);
+  THR_REQUIRE(h, tie_mode == THR_TIE_INSERTION || tie_mode == THR_TIE_CHUNK_ID, "thr_fuse: unknown tie_mode %d", tie_mode);
+  THR_REQUIRE(h, weights && out_ids && out_rrf && out_ranks && out_count, "thr_fuse: NULL weights/output");
+  THR_REQUIRE(h, (lex_ids == nullptr || lex_off) && (sem_ids == nullptr || sem_off) && (gr_ids == nullptr || gr_off),
+              "thr_fuse: ids without offsets");
+  THR_REQUIRE(h, max_out >= 1, "thr_fuse: max_out < 1");
+  THR_REQUIRE(h, rrf_k >= 0, "thr_fuse: rrf_k < 0");
+  FuseArgs a;
+  a.ids[0] = lex_ids; a.off[0] = lex_off; a.sc[0] = lex_sc;
+  a.ids[1] = sem_ids; a.off[1] = sem_off; a.sc[1] = sem_sc;
+  a.ids[2] = gr_ids;  a.off[2] = gr_off;  a.sc[2] = gr_sc;
+  a.weights = weights; a.rrf_k = rrf_k; a.safety_thr = safety_thr; a.alpha = alpha;
+  a.denoise = denoise; a.top_k = top_k; a.max_out = max_out; a.tie_mode = tie_mode;
+  a.out_ids = out_ids; a.out_rrf = out_rrf; a.out_ranks = out_ranks; a.out_raw = out_raw;
+  a.out_count = out_count; a.status = h->d_status;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (variant == THR_FUSE_RAG2) fuse_kernel<THR_FUSE_RAG2><<<B, kFuseThreads, 0, s>>>(a);
+  else if (variant == THR_FUSE_LIB) fuse_kernel<THR_FUSE_LIB><<<B, kFuseThreads, 0, s>>>(a);
+  else fuse_kernel<THR_FUSE_RAG1><<<B, kFuseThreads, 0, s>>>(a);
+  THR_CHECK_LAUNCH(h, "fuse_kernel");
+  return THR_OK;
+}
+
+int thr_safety(thr_handle* h, int B, const int32_t* off, const double* rerank,
+               const uint8_t* has_rerank, const double* rrf, double threshold, double alpha,
+               int top_k, uint8_t* keep, uint8_t* refused, double* max_score, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, B >= 0, "thr_safety: B < 0");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, off && rrf && keep && refused && max_score, "thr_safety: NULL argument");
+  THR_REQUIRE(h, has_rerank == nullptr || rerank != nullptr, "thr_safety: has_rerank without rerank");
+  safety_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, off, rerank, has_rerank, rrf, threshold,
+                                                               alpha, top_k, keep, refused, max_score);
+  THR_CHECK_LAUNCH(h, "safety_kernel");
+  return THR_OK;
+}
+
+int thr_merge_topk(thr_handle* h, const double* scores, const int64_t* ids, const int32_t* counts,
+                   int G, int B, int k_in, int k_out, double* out_scores, int64_t* out_ids,
+                   int32_t* out_count, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, G >= 1 && B >= 0 && k_in >= 1 && k_out >= 1, "thr_merge_topk: bad sizes");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, (int64_t)G * k_in <= kMergeMax, "thr_merge_topk: G*k_in = %lld exceeds %d",
+              (long long)G * k_in, kMergeMax);
+  THR_REQUIRE(h, k_out <= 256, "thr_merge_topk: k_out > 256");
+  THR_REQUIRE(h, scores && ids && out_scores && out_ids && out_count, "thr_merge_topk: NULL argument");
+  merge_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, ids, counts, G, B, k_in, k_out, out_scores,
+                                                    out_ids, out_count);
+  THR_CHECK_LAUNCH(h, "merge_kernel");
+  return THR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""Engine: one libthr handle bound to one GPU, driven with torch tensors.
+
+torch is plumbing here (device memory, streams); every scoring step is a C-ABI call into the
+hand-written sm_100a kernels.  All methods enqueue on the current torch CUDA stream and return
+device tensors; call ``sync()`` to surface device-side failures.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device: int | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("triple_hybrid_rag_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("Engine requires a cuda device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self._lib = lib
+        h = C.c_void_p()
+        rc = lib.thr_create(self.device.index, C.byref(h))
+        if rc != 0:
+            raise _lib.ThrError(rc, lib.thr_last_error(None).decode())
+        self._h = h
+        self._keep = {}  # tensors the C side references (indices are not copied)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.thr_destroy(self._h)
+            self._h = None
+            self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise _lib.ThrError(rc, self._lib.thr_last_error(self._h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self._check(self._lib.thr_sync(self._h, self._stream()))
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.thr_launch_count(self._h))
+
+    def _dev(self, t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name}: expected a torch.Tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name}: tensor is on {t.device}, engine is on {self.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name}: dtype {t.dtype}, expected {dtype}")
+        return t.contiguous()
+
+    # -- K1 dense ---------------------------------------------------------------------------
+    def dense_index_set(self, X: torch.Tensor, id_base: int = 0):
+        X = self._dev(X, torch.bfloat16, "X")
+        if X.dim() != 2:
+            raise ValueError("X must be [N, D]")
+        self._keep["X"] = X
+        self._check(self._lib.thr_dense_index_set(self._h, _ptr(X), X.shape[0], X.shape[1], id_base))
+
+    def dense_topk(self, Q: torch.Tensor, k: int, margin: int = 28
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> ids [B,k] int64, scores [B,k] float64, count [B] int32, gap [B] float32."""
+        Q = self._dev(Q, torch.bfloat16, "Q")
+        B = Q.shape[0]
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((B, k), dtype=torch.float64, device=self.device)
+        cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+        gap = torch.empty((B,), dtype=torch.float32, device=self.device)
+        self._check(self._lib.thr_dense_topk(self._h, _ptr(Q), B, k, margin, _ptr(ids), _ptr(sc), _ptr(cnt),
+                                             _ptr(gap), self._stream()))
+        return ids, sc, cnt, gap
+
+    # -- K2 BM25 ----------------------------------------------------------------------------
+    def bm25_index_set(self, blk_ptr: torch.Tensor, postings: torch.Tensor, idf: torch.Tensor, n_docs: int,
+                       blk_docs: int, V: int, id_base: int = 0):
+        blk_ptr = self._dev(blk_ptr, torch.int64, "blk_ptr")
+        postings = self._dev(postings, torch.int32, "postings")  # [nnz + pad, 2] raw {doc, impact bits}
+        idf = self._dev(idf, torch.float32, "idf")
+        n_blk = (n_docs + blk_docs - 1) // blk_docs
+        if blk_ptr.numel() != n_blk * (V + 1):
+            raise ValueError("blk_ptr must have n_blk * (V + 1) entries")
+        self._keep.update(blk_ptr=blk_ptr, postings=postings, idf=idf)
+        self._check(self._lib.thr_bm25_index_set(self._h, _ptr(blk_ptr), _ptr(postings), _ptr(idf), n_docs, n_blk,
+                                                 blk_docs, V, id_base))
+
+    def bm25_topk(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> ids [B,k] int64, scores [B,k] float32, count [B] int32."""
+        q_terms = self._dev(q_terms, torch.int32, "q_terms")
+        q_off = self._dev(q_off, torch.int32, "q_off")
+        B = q_off.numel() - 1
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self._check(self._lib.thr_bm25_topk(self._h, _ptr(q_terms), _ptr(q_off), B, k, _ptr(ids), _ptr(sc),
+                                            _ptr(cnt), self._stream()))
+        return ids, sc, cnt
+
+    # -- K3 fusion --------------------------------------------------------------------------
+    def fuse(self, variant: int, B: int, lists: Sequence[Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]]],
+             weights: torch.Tensor, rrf_k: int = 60, safety_thr: float = 0.0, alpha: float = 0.0,
+             denoise: bool = False, top_k: int = 0, max_out: Optional[int] = None,
+             tie_mode: int = _lib.TIE_INSERTION, want_raw: bool = False):
+        """lists: three entries (lexical, semantic, graph), each None or (ids int64, off int32 [B+1], scores f64|None).
+        -> ids [B,max_out], rrf [B,max_out] f64, ranks [B,max_out,3] i32, raw [B,max_out,3] f64|None, count [B]."""
+        assert len(lists) == 3
+        args = []
+        longest = 0
+        for i, l in enumerate(lists):
+            if l is None:
+                args += [None, None, None]
+                continue
+            ids, off, sc = l
+            ids = self._dev(ids, torch.int64, f"ids[{i}]")
+            off = self._dev(off, torch.int32, f"off[{i}]")
+            if off.numel() != B + 1:
+                raise ValueError("off must have B + 1 entries")
+            if sc is not None:
+                sc = self._dev(sc, torch.float64, f"scores[{i}]")
+            args += [ids, off, sc]
+            longest += 256
+        weights = self._dev(weights, torch.float64, "weights")
+        if tuple(weights.shape) != (B, 3):
+            raise ValueError("weights must be [B, 3] (lexical, semantic, graph)")
+        if max_out is None:
+            max_out = top_k if top_k > 0 else max(longest, 1)
+        o_ids = torch.empty((B, max_out), dtype=torch.int64, device=self.device)
+        o_rrf = torch.empty((B, max_out), dtype=torch.float64, device=self.device)
+        o_rk = torch.empty((B, max_out, 3), dtype=torch.int32, device=self.device)
+        o_raw = torch.empty((B, max_out, 3), dtype=torch.float64, device=self.device) if want_raw else None
+        o_cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self._check(self._lib.thr_fuse(self._h, variant, tie_mode, B, *[_ptr(x) for x in args], _ptr(weights), rrf_k,
+                                       float(safety_thr), float(alpha), int(bool(denoise)), int(top_k), int(max_out),
+                                       _ptr(o_ids), _ptr(o_rrf), _ptr(o_rk), _ptr(o_raw), _ptr(o_cnt), self._stream()))
+        return o_ids, o_rrf, o_rk, o_raw, o_cnt
+
+    def safety(self, off: torch.Tensor, rrf: torch.Tensor, rerank: Optional[torch.Tensor],
+               has_rerank: Optional[torch.Tensor], threshold: float, alpha: float, top_k: int):
+        """-> keep [n] uint8, refused [B] uint8, max_score [B] f64."""
+        off = self._dev(off, torch.int32, "off")
+        rrf = self._dev(rrf, torch.float64, "rrf")
+        if rerank is not None:
+            rerank = self._dev(rerank, torch.float64, "rerank")
+            has_rerank = self._dev(has_rerank, torch.uint8, "has_rerank")
+        B = off.numel() - 1
+        keep = torch.zeros((max(rrf.numel(), 1),), dtype=torch.uint8, device=self.device)
+        refused = torch.empty((B,), dtype=torch.uint8, device=self.device)
+        mx = torch.empty((B,), dtype=torch.float64, device=self.device)
+        self._check(self._lib.thr_safety(self._h, B, _ptr(off), _ptr(rerank), _ptr(has_rerank), _ptr(rrf),
+                                         float(threshold), float(alpha), int(top_k), _ptr(keep), _ptr(refused),
+                                         _ptr(mx), self._stream()))
+        return keep[: rrf.numel()], refused, mx
+
+    # -- K4 MaxSim --------------------------------------------------------------------------
+    def maxsim(self, Qtok: torch.Tensor, Dtok: torch.Tensor, cand: torch.Tensor,
+               q_len: Optional[torch.Tensor] = None, d_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Qtok [B,Tq,d] bf16, Dtok [n_docs,Td,d] bf16, cand [B,C] int64 -> scores [B,C] float32."""
+        Qtok = self._dev(Qtok, torch.bfloat16, "Qtok")
+        Dtok = self._dev(Dtok, torch.bfloat16, "Dtok")
+        cand = self._dev(cand, torch.int64, "cand")
+        if q_len is not None:
+            q_len = self._dev(q_len, torch.int32, "q_len")
+        if d_len is not None:
+            d_len = self._dev(d_len, torch.int32, "d_len")
+        B, Tq, d = Qtok.shape
+        n_docs, Td, d2 = Dtok.shape
+        if d2 != d or cand.shape[0] != B:
+            raise ValueError("shape mismatch")
+        Cc = cand.shape[1]
+        out = torch.empty((B, Cc), dtype=torch.float32, device=self.device)
+        self._check(self._lib.thr_maxsim(self._h, _ptr(Qtok), _ptr(q_len), B, Tq, d, _ptr(Dtok), _ptr(d_len), n_docs,
+                                         Td, _ptr(cand), Cc, _ptr(out), self._stream()))
+        return out
+
+    # -- K5 merge ---------------------------------------------------------------------------
+    def merge_topk(self, scores: torch.Tensor, ids: torch.Tensor, counts: Optional[torch.Tensor], k_out: int):
+        """scores [G,B,k] f64, ids [G,B,k] i64, counts [G,B] i32 -> scores [B,k_out], ids [B,k_out], count [B]."""
+        scores = self._dev(scores, torch.float64, "scores")
+        ids = self._dev(ids, torch.int64, "ids")
+        if counts is not None:
+            counts = self._dev(counts, torch.int32, "counts")
+        G, B, k_in = scores.shape
+        o_sc = torch.empty((B, k_out), dtype=torch.float64, device=self.device)
+        o_ids = torch.empty((B, k_out), dtype=torch.int64, device=self.device)
+        o_cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self._check(self._lib.thr_merge_topk(self._h, _ptr(scores), _ptr(ids), _ptr(counts), G, B, k_in, k_out,
+                                             _ptr(o_sc), _ptr(o_ids), _ptr(o_cnt), self._stream()))
+        return o_sc, o_ids, o_cnt
