@@ -1,0 +1,77 @@
+"""K1 parity: tcgen05 dense top-k vs the fp64 oracle — ids bit-exact, scores within 1e-3 relative
+(north_star's tolerance; measured error is ~1e-15 because survivors are re-scored in fp64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense as od
+from triple_hybrid_rag_b200 import synth
+from triple_hybrid_rag_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-3
+
+
+def _check(engine, X, Q, k, margin=28, id_base=0):
+    engine.dense_index_set(X.to(engine.device), id_base=id_base)
+    ids, sc, cnt, gap = engine.dense_topk(Q.to(engine.device), k, margin)
+    engine.sync()
+    want_i, want_s = od.dense_topk(Q.float().numpy(), X.float().numpy(), k, id_base=id_base)
+    ids, sc, cnt, gap = ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy(), gap.cpu().numpy()
+    n = min(k, X.shape[0])
+    assert (cnt == n).all()
+    assert np.array_equal(ids, want_i), f"{(ids != want_i).sum()} of {ids.size} ids differ"
+    assert np.allclose(sc[:, :n], want_s[:, :n], rtol=REL_TOL, atol=1e-6)
+    return gap
+
+
+@pytest.mark.parametrize("N,D,B,k", [(10_000, 1536, 256, 50), (5_000, 128, 7, 10), (777, 64, 1, 100),
+                                     (70_000, 1024, 300, 100)])
+def test_dense_topk_matches_oracle(engine, N, D, B, k):
+    X = synth.dense_block(0, N, D)
+    Q = synth.dense_queries(B, D, X)
+    gap = _check(engine, X, Q, k)
+    # certificate: the k-th exact score clears everything that was not re-scored by far more than
+    # the fp32 accumulation error of a unit-vector dot product
+    assert (gap > 2e-6).all() or N <= k + 28
+
+
+def test_dense_small_corpus_and_id_base(engine):
+    X = synth.dense_block(1, 40, 64)
+    Q = synth.dense_queries(3, 64, X)
+    _check(engine, X, Q, 50, id_base=1_000_000)
+
+
+def test_dense_duplicate_rows_tie_by_id(engine):
+    X = synth.dense_block(2, 3000, 128)
+    X[100:400] = X[7]          # 301 identical chunks: exact score ties, must come out in id order
+    Q = synth.dense_queries(9, 128, X)
+    Q[0] = X[7]
+    _check(engine, X, Q, 100)
+
+
+def test_dense_single_cta_path_agrees():
+    """THR_DENSE_CTA_GROUP=1 (M=128 single-CTA MMA) must give the same answer as the CTA-pair path."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    os.environ["THR_DENSE_CTA_GROUP"] = "1"
+    try:
+        eng = Engine(0)
+        X = synth.dense_block(0, 20_000, 256)
+        Q = synth.dense_queries(130, 256, X)
+        _check(eng, X, Q, 100)
+        eng.close()
+    finally:
+        del os.environ["THR_DENSE_CTA_GROUP"]
+
+
+def test_dense_errors(engine):
+    from triple_hybrid_rag_b200._lib import ThrError
+    with pytest.raises(ThrError):
+        engine.dense_index_set(torch.zeros((10, 100), dtype=torch.bfloat16, device=engine.device))  # D % 64
+    X = synth.dense_block(0, 1000, 64).to(engine.device)
+    engine.dense_index_set(X)
+    with pytest.raises(ThrError):
+        engine.dense_topk(torch.zeros((2, 64), dtype=torch.bfloat16, device=engine.device), 250, 28)  # k+margin

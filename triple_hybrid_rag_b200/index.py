@@ -1,0 +1,130 @@
+"""Resident indexes for the hot path.
+
+BM25Index builds the blocked inverted index libthr's K2 kernel reads (layout in include/thr.h):
+documents are cut into ranges of `blk_docs`, postings are ordered (range, term, doc) and stored as
+{uint32 doc, float32 impact}.  Building is torch plumbing (sort / bincount / cumsum) and runs on
+whatever device the inputs live on; it is the step before the hot path.
+The BM25 formula is the one oracle/bm25.py states; idf is always computed with numpy on the host
+so that both sides use the same libm.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def bm25_idf(df: torch.Tensor, n_docs: int) -> torch.Tensor:
+    d = df.detach().cpu().numpy().astype(np.float64)
+    idf = np.log(1.0 + (n_docs - d + 0.5) / (d + 0.5)).astype(np.float32)
+    return torch.from_numpy(idf)
+
+
+def bm25_impacts(tf: torch.Tensor, dl: torch.Tensor, avgdl: float, k1: float, b: float) -> torch.Tensor:
+    tf = tf.to(torch.float64)
+    norm = k1 * (1.0 - b + b * dl.to(torch.float64) / float(avgdl))
+    return (tf * (k1 + 1.0) / (tf + norm)).to(torch.float32)
+
+
+@dataclass
+class BM25Index:
+    blk_ptr: torch.Tensor    # int64 [n_blk * (V + 1)]
+    postings: torch.Tensor   # int32 [nnz + 2, 2]: {doc (u32 bits), impact (f32 bits)}, 16 B tail padding
+    idf: torch.Tensor        # float32 [V]
+    df: torch.Tensor         # int64 [V] (this shard)
+    n_docs: int
+    blk_docs: int
+    V: int
+    nnz: int
+    k1: float = 1.2
+    b: float = 0.75
+    avgdl: float = 0.0
+
+    @property
+    def n_blk(self) -> int:
+        return (self.n_docs + self.blk_docs - 1) // self.blk_docs
+
+    @staticmethod
+    def build(doc: torch.Tensor, term: torch.Tensor, tf: torch.Tensor, doc_len: torch.Tensor, V: int,
+              blk_docs: int = 16384, k1: float = 1.2, b: float = 0.75, avgdl: Optional[float] = None,
+              idf: Optional[torch.Tensor] = None, n_docs_global: Optional[int] = None) -> "BM25Index":
+        """doc/term/tf: COO of (local doc id, term id, term frequency); doc_len [n_docs]."""
+        dev = doc.device
+        n_docs = int(doc_len.shape[0])
+        R = int(blk_docs)
+        n_blk = (n_docs + R - 1) // R
+        doc = doc.to(torch.int64)
+        term = term.to(torch.int64)
+        if avgdl is None:
+            avgdl = float(doc_len.to(torch.float64).mean().item())
+        imp = bm25_impacts(tf, doc_len.to(dev)[doc], avgdl, k1, b)
+        blk_key = (doc // R) * V + term
+        order = torch.argsort(blk_key * R + (doc % R))
+        counts = torch.bincount(blk_key, minlength=n_blk * V)
+        excl = torch.zeros(n_blk * V + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=excl[1:])
+        ptr = torch.empty((n_blk, V + 1), dtype=torch.int64, device=dev)
+        ptr[:, :V] = excl[:-1].view(n_blk, V)
+        ptr[:, V] = excl[V::V]
+        nnz = int(doc.numel())
+        post = torch.zeros((nnz + 2, 2), dtype=torch.int32, device=dev)
+        post[:nnz, 0] = doc[order].to(torch.int32)  # n_docs < 2^31 per shard here; kernel reads u32
+        post[:nnz, 1] = imp[order].view(torch.int32)
+        df = torch.bincount(term, minlength=V)
+        if idf is None:
+            idf = bm25_idf(df, n_docs_global or n_docs)
+        return BM25Index(ptr.reshape(-1), post, idf.to(torch.float32).to(dev), df, n_docs, R, V, nnz, k1, b, avgdl)
+
+    @staticmethod
+    def concat(parts: Sequence["BM25Index"], idf: Optional[torch.Tensor] = None,
+               n_docs_global: Optional[int] = None) -> "BM25Index":
+        """Concatenate indexes of consecutive doc ranges (every part but the last must hold a whole
+        number of blocks; doc ids inside each part are local to the part and get rebased here)."""
+        p0 = parts[0]
+        dev = p0.postings.device
+        ptrs, posts = [], []
+        base_post, base_doc = 0, 0
+        df = torch.zeros_like(p0.df)
+        for i, p in enumerate(parts):
+            assert p.blk_docs == p0.blk_docs and p.V == p0.V
+            if i + 1 < len(parts):
+                assert p.n_docs % p.blk_docs == 0, "only the last part may end with a partial block"
+            ptrs.append(p.blk_ptr + base_post)
+            pp = p.postings[:p.nnz].clone()
+            pp[:, 0] += base_doc
+            posts.append(pp)
+            base_post += p.nnz
+            base_doc += p.n_docs
+            df += p.df
+        posts.append(torch.zeros((2, 2), dtype=torch.int32, device=dev))
+        if idf is None:
+            idf = bm25_idf(df, n_docs_global or base_doc)
+        return BM25Index(torch.cat(ptrs), torch.cat(posts), idf.to(torch.float32).to(dev), df, base_doc,
+                         p0.blk_docs, p0.V, base_post, p0.k1, p0.b, p0.avgdl)
+
+    def to(self, device) -> "BM25Index":
+        return BM25Index(self.blk_ptr.to(device), self.postings.to(device), self.idf.to(device), self.df.to(device),
+                         self.n_docs, self.blk_docs, self.V, self.nnz, self.k1, self.b, self.avgdl)
+
+    def algorithmic_bytes(self, queries: Sequence[Sequence[int]]) -> int:
+        """sum over queries and terms of df_t * 8 B (+ 16 B of pointers per term and block)."""
+        df = self.df.cpu()
+        tot = 0
+        for q in queries:
+            for t in q:
+                if 0 <= t < self.V:
+                    tot += int(df[t]) * 8 + 16 * self.n_blk
+        return tot
+
+
+def pack_queries(queries: Sequence[Sequence[int]], device) -> tuple:
+    """Ragged term-id lists -> (q_terms int32, q_off int32 [B+1]) on `device`."""
+    off = [0]
+    flat: List[int] = []
+    for q in queries:
+        flat.extend(int(t) for t in q)
+        off.append(len(flat))
+    return (torch.tensor(flat if flat else [0], dtype=torch.int32, device=device)[: max(len(flat), 1)],
+            torch.tensor(off, dtype=torch.int32, device=device))
