@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — QPS (batch 256) of the triple-hybrid top-100 step over 10M x 1536 chunks.
+
+One step = one batch of 256 queries through dense top-100 (K1) + BM25 top-100 (K2) + weighted RRF
+fusion with the synthetic graph list (K3), corpus resident in HBM.  With --gpus N > 1 (torchrun)
+the corpus is sharded by chunk-id range over the ranks (strong scaling: the total corpus is fixed),
+local top-k lists are all-gathered over NCCL and merged (K5) before the fusion.
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every key).  `--impl reference` times the CPU
+port of the same step on the host cores (the reference's own path needs Postgres/HTTP services).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "QPS (batch 256) triple-hybrid top-100 over 10M x 1536 chunks"
+ALIGN = 16384  # shard boundaries are BM25 block boundaries
+GEN_DOCS = 262144
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=int(os.environ.get("THR_BENCH_CHUNKS", 10_000_000)))
+    ap.add_argument("--dim", type=int, default=int(os.environ.get("THR_BENCH_DIM", 1536)))
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--vocab", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("THR_BENCH_CPU_SAMPLE", 262144)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_config(args, world: int):
+    N, D, B, k, V = args.chunks, args.dim, args.batch, args.k, args.vocab
+    return {"workload": f"triple-hybrid top-{k}: dense {N}x{D} bf16 + BM25 {N} docs V={V} (Zipf) + weighted RRF "
+                        f"1.0/0.8/0.7 with a synthetic 50-id graph list, batch {B}",
+            "chunks": N, "dim": D, "batch": B, "k": k, "channel_depths": [k, k, 50],
+            "parallelism": f"chunk-sharded x{world}" if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (per-rank corpus shard >> 126 MB); no explicit flush",
+            "rerank": "MaxSim (K4) is not part of this step; see tests and DESIGN.md"}
+
+
+def shard_bounds(n: int, world: int):
+    b = [0]
+    for r in range(1, world):
+        b.append(min(n, (n * r // world) // ALIGN * ALIGN))
+    b.append(n)
+    return b
+
+
+def cpu_baseline(args, threads=None):
+    """CPU port on a bounded sample of the same workload; returns the cpu_baseline dict + QPS."""
+    import numpy as np
+    import torch
+    from oracle import bm25 as ob
+    from oracle import cpu_pipeline as cp
+    from triple_hybrid_rag_b200 import synth
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    ns = min(args.cpu_sample, args.chunks)
+    X = synth.dense_rows(0, ns, args.dim).float()
+    Q = synth.dense_queries(args.batch, args.dim, X[: max(1, ns // 8)]).float()
+    doc, term, tf, L = synth.bm25_block_coo(0, ns, V=args.vocab)
+    index = ob.CsrIndex.from_coo(doc.numpy(), term.numpy(), tf.numpy(), L.numpy(), args.vocab)
+    queries = synth.bm25_queries(args.batch, V=args.vocab)
+    g = np.random.default_rng(77).integers(0, ns, size=(args.batch, 50))
+    return X, Q, index, queries, g, ns, cores
+
+
+def cpu_time_step(args, state):
+    from oracle import cpu_pipeline as cp
+    X, Q, index, queries, g, ns, cores = state
+    t = cp.step(Q, X, index, queries, g, args.k, args.k)
+    scale = args.chunks / ns
+    total = t["dense"] * scale + t["bm25"] * scale + t["fuse"]
+    return total, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    state = cpu_baseline(args)
+    ns, cores = state[5], state[6]
+    for _ in range(min(args.warmup, 1)):
+        cpu_time_step(args, state)
+    steps = max(1, min(args.steps, 5))
+    tot = []
+    for _ in range(steps):
+        t, _parts = cpu_time_step(args, state)
+        tot.append(t)
+    sec = statistics.median(tot)
+    qps = args.batch / sec
+    sample = (f"each step runs the batch of {args.batch} queries over the first {ns} chunks/docs of the corpus and is "
+              f"scaled x{args.chunks / ns:.1f} (dense and BM25 are linear in corpus size); fusion unscaled")
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(make_config(args, 1), parallelism=f"host CPU, {cores} threads"),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from triple_hybrid_rag_b200 import synth
+    from triple_hybrid_rag_b200.engine import Engine
+    from triple_hybrid_rag_b200.index import BM25Index, bm25_idf, pack_queries
+    from triple_hybrid_rag_b200.pipeline import TripleHybridSearcher
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    N, D, B, k, V = args.chunks, args.dim, args.batch, args.k, args.vocab
+
+    eng = Engine(dev)
+    searcher = TripleHybridSearcher(eng, group)
+    bounds = shard_bounds(N, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+
+    # ---- resident corpus (generated on the device, block-wise) ----
+    t_setup = time.time()
+    X = synth.dense_rows(lo, hi, D, device=dev)
+    searcher.set_dense(X, id_base=lo)
+    n_gen = (N + GEN_DOCS - 1) // GEN_DOCS
+    lens_total = 0
+    for gb in range(n_gen):
+        rows = min(GEN_DOCS, N - gb * GEN_DOCS)
+        lens_total += int(synth.bm25_doc_lens(gb, rows, device=dev).sum().item())
+    avgdl = lens_total / N
+    parts = []
+    for gb in range(n_gen):
+        g_lo, g_hi = gb * GEN_DOCS, min(N, (gb + 1) * GEN_DOCS)
+        a, b = max(lo, g_lo), min(hi, g_hi)
+        if a >= b:
+            continue
+        doc, term, tf, L = synth.bm25_block_coo(gb, g_hi - g_lo, V=V, device=dev)
+        if a > g_lo or b < g_hi:
+            m = (doc >= a - g_lo) & (doc < b - g_lo)
+            doc, term, tf = doc[m] - (a - g_lo), term[m], tf[m]
+            L = L[a - g_lo:b - g_lo]
+        parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=ALIGN, avgdl=avgdl,
+                                     idf=torch.zeros(V), n_docs_global=N))
+        del doc, term, tf, L
+    df = sum(p.df for p in parts)
+    if world > 1:
+        dist.all_reduce(df, group=group)
+    idf = bm25_idf(df, N)
+    index = BM25Index.concat(parts, idf=idf) if len(parts) > 1 else parts[0]
+    index.idf = idf.to(dev)
+    del parts
+    searcher.set_bm25(index, id_base=lo)
+    torch.cuda.empty_cache()
+
+    # ---- queries (replicated) ----
+    if rank == 0:
+        Q = synth.dense_queries(B, D, X, n_plant=max(1, min(hi - lo, N // 8)))
+    else:
+        Q = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+    if world > 1:
+        dist.broadcast(Q, 0, group=group)
+    queries = synth.bm25_queries(B, V=V)
+    q_terms, q_off = pack_queries(queries, dev)
+    out0 = searcher.search(Q, q_terms, q_off, None, k_sem=k, k_lex=k, top_k=k)
+    eng.sync()
+    graph = synth.graph_lists(out0.sem_ids, out0.lex_ids, N, length=50).to(dev)
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timed loop ----
+    for _ in range(max(args.warmup, 3)):
+        searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+    eng.sync()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    l0 = eng.launches
+    eng.prof_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = eng.prof_read()
+    eng.prof_enable(False)
+    launches = eng.launches - l0
+    eng.sync()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms_step = float(t.item()) / args.steps
+    qps = B / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> search -> pinned host outputs, every step ----
+    hQ, hT, hO, hG = (x.cpu().pin_memory() for x in (Q, q_terms, q_off, graph))
+    for _ in range(2):
+        searcher.search_host(hQ, hT, hO, hG, k_sem=k, k_lex=k, top_k=k)
+    lat = []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s0 = time.perf_counter()
+        _, _, _, h2d, d2h = searcher.search_host(hQ, hT, hO, hG, k_sem=k, k_lex=k, top_k=k)
+        lat.append(time.perf_counter() - s0)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX, group=group)
+    e2e_qps = B * args.steps / float(te.item())
+    # batch-1 latency (p50 of a single query end to end)
+    q1 = pack_queries(queries[:1], "cpu")
+    h1 = (hQ[:1].clone().pin_memory(), q1[0].pin_memory(), q1[1].pin_memory(), hG[:1].clone().pin_memory())
+    lat1 = []
+    for i in range(23):
+        s0 = time.perf_counter()
+        searcher.search_host(*h1, k_sem=k, k_lex=k, top_k=k)
+        if i >= 3:
+            lat1.append(time.perf_counter() - s0)
+    clk = clocks.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    burst, sustained, hbm, which = peaks()
+    dense_ms, dense_n = prof.get("dense_score", (0.0, 0))
+    dense_avg = dense_ms / max(dense_n, 1)
+    flops = 2.0 * B * (hi - lo) * D
+    achieved = flops / (dense_avg * 1e-3) / 1e12 if dense_avg > 0 else 0.0
+    x_bytes = float(hi - lo) * D * 2
+    stages = {n: round(ms / max(c, 1), 4) for n, (ms, c) in prof.items()}
+    bm25_bytes = index.algorithmic_bytes(queries)
+    bm25_ms = stages.get("bm25", 0.0)
+    line = {
+        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": make_config(args, world),
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "latency": {"p50_ms_batch256_e2e": statistics.median(lat) * 1e3, "p50_ms_batch1_e2e": statistics.median(lat1) * 1e3},
+        "stages_ms": stages,
+        "roofline": {"kernel": "dense_score_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained,
+                     "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None, "traffic": None,
+                     "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
+                     "frac_of_burst": achieved / burst if burst else None,
+                     "hbm_gbs": x_bytes / (dense_avg * 1e-3) / 1e9 if dense_avg > 0 else 0.0,
+                     "hbm_frac": (x_bytes / (dense_avg * 1e-3) / 1e9) / hbm if dense_avg > 0 else None,
+                     "launch_ms": dense_avg, "launches": dense_n},
+        "bm25_roofline": {"kernel": "bm25_kernel", "bound": "hbm", "algorithmic_bytes": bm25_bytes,
+                          "achieved": bm25_bytes / (bm25_ms * 1e-3) / 1e9 if bm25_ms > 0 else 0.0, "peak": hbm,
+                          "unit": "GB/s", "frac": (bm25_bytes / (bm25_ms * 1e-3) / 1e9) / hbm if bm25_ms > 0 else None},
+        "setup_s": round(setup_s, 1),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            state = cpu_baseline(args)
+            cpu_time_step(args, state)
+            sec, parts = cpu_time_step(args, state)
+            ns, cores = state[5], state[6]
+            line["cpu_baseline"] = {"value": B / sec, "unit": "queries/s", "cores": cores, "kind": "port",
+                                    "sample": f"batch {B} over the first {ns} chunks/docs, dense+BM25 scaled x{N / ns:.1f}; "
+                                              f"stage seconds on the sample: {{'dense': {parts['dense']:.3f}, "
+                                              f"'bm25': {parts['bm25']:.3f}, 'fuse': {parts['fuse']:.3f}}}"}
+        except Exception as e:  # the baseline is a reported extra; never lose the GPU numbers over it
+            line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": None, "kind": "port",
+                                    "sample": f"failed: {e!r}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

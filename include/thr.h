@@ -67,6 +67,19 @@ int thr_sync(thr_handle* h, void* stream);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t thr_launch_count(const thr_handle* h);
 
+/* Per-kernel device timing.  When enabled, every kernel launch is bracketed by CUDA events on the
+ * launch stream; thr_prof_read synchronises the device, adds up the elapsed times recorded for
+ * `slot` since the last thr_prof_reset and returns the number of launches.  This is how bench.py
+ * measures the dominant kernel inside the timed step (roofline.achieved). */
+enum {
+  THR_PROF_DENSE_SCORE = 0, THR_PROF_DENSE_FINALIZE = 1, THR_PROF_BM25 = 2, THR_PROF_FUSE = 3,
+  THR_PROF_MAXSIM = 4, THR_PROF_MERGE = 5, THR_PROF_SAFETY = 6, THR_PROF_BM25_PREP = 7,
+  THR_PROF_SLOTS = 8
+};
+int thr_prof_enable(thr_handle* h, int on);
+int thr_prof_reset(thr_handle* h);
+int thr_prof_read(thr_handle* h, int slot, double* total_ms, int64_t* launches);
+
 /* ---- K1: semantic channel — exact dense top-k ------------------------------------
  * Replaces RAG2Retriever._semantic_search -> RPC rag2_semantic_search
  *   src/voice_agent/rag2/retrieval.py:294-314
@@ -135,7 +148,8 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
  *   THR_FUSE_RAG1: HybridSearcher._rrf_fusion  src/voice_agent/retrieval/hybrid_search.py:460-501
  *
  * Three ranked id lists per query in CSR form (ids int64, off int32 [B+1]); rank = 1 + position.
- * A NULL ids pointer means the channel is absent for every query.  *_sc are the channels' raw
+ * Negative ids are padding and ignored, so a fixed-width [B,k] top-k result (-1 past its count) can
+ * be passed as is with off[q] = q*k.  A NULL ids pointer means the channel is absent for every query.  *_sc are the channels' raw
  * scores (double, nullable; only THR_FUSE_LIB reads them).  weights [B,3] double in the order
  * lexical, semantic, graph.  Each list may be at most 256 long.
  *

@@ -18,6 +18,7 @@ THR_EINVAL, THR_ECUDA, THR_EUNSUPPORTED, THR_ENOINDEX, THR_EOVERFLOW, THR_ETIMEO
 FUSE_RAG2, FUSE_LIB, FUSE_RAG1 = 0, 1, 2
 TIE_INSERTION, TIE_CHUNK_ID = 0, 1
 ABI_VERSION = 1
+PROF_SLOTS = ("dense_score", "dense_finalize", "bm25", "fuse", "maxsim", "merge", "safety", "bm25_prep")
 
 _p, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
@@ -29,6 +30,9 @@ SIGNATURES = {
     "thr_last_error": (C.c_char_p, [_p]),
     "thr_sync": (_i, [_p, _p]),
     "thr_launch_count": (_i64, [_p]),
+    "thr_prof_enable": (_i, [_p, _i]),
+    "thr_prof_reset": (_i, [_p]),
+    "thr_prof_read": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "thr_dense_index_set": (_i, [_p, _p, _i64, _i, _i64]),
     "thr_dense_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "thr_bm25_index_set": (_i, [_p, _p, _p, _p, _i64, C.c_int32, C.c_int32, C.c_int32, _i64]),

@@ -38,6 +38,17 @@ void* thr_scratch(thr_handle* h, size_t bytes) {
   return p;
 }
 
+int thr_prof_begin(thr_handle* h, int slot, cudaStream_t s) {
+  if (!h->prof_on || h->prof_n >= kProfMax) return -1;
+  int i = h->prof_n++;
+  h->prof_slot[i] = (unsigned char)slot;
+  cudaEventRecord(h->prof_ev[2 * i], s);
+  return i;
+}
+void thr_prof_end(thr_handle* h, int token, cudaStream_t s) {
+  if (token >= 0) cudaEventRecord(h->prof_ev[2 * token + 1], s);
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -119,8 +130,51 @@ int thr_destroy(thr_handle* h) {
   thr_dense_state_free(h);
   thr_bm25_state_free(h);
   if (h->scratch) cudaFree(h->scratch);
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(h->prof_ev[i]);
+    free(h->prof_ev);
+    free(h->prof_slot);
+  }
   if (h->h_status) cudaFreeHost(h->h_status);
   free(h);
+  return THR_OK;
+}
+
+int thr_prof_enable(thr_handle* h, int on) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  if (on && !h->prof_ev) {
+    h->prof_ev = (cudaEvent_t*)calloc(2 * kProfMax, sizeof(cudaEvent_t));
+    h->prof_slot = (unsigned char*)calloc(kProfMax, 1);
+    if (!h->prof_ev || !h->prof_slot) return thr_fail(h, THR_ENOMEM, "out of host memory");
+    for (int i = 0; i < 2 * kProfMax; ++i) THR_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+  }
+  h->prof_on = on ? 1 : 0;
+  return THR_OK;
+}
+
+int thr_prof_reset(thr_handle* h) {
+  if (!h) return THR_EINVAL;
+  h->prof_n = 0;
+  return THR_OK;
+}
+
+int thr_prof_read(thr_handle* h, int slot, double* total_ms, int64_t* launches) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, slot >= 0 && slot < THR_PROF_SLOTS && total_ms && launches, "thr_prof_read: bad argument");
+  THR_CUDA(h, cudaDeviceSynchronize());
+  double tot = 0.0;
+  int64_t n = 0;
+  for (int i = 0; i < h->prof_n; ++i) {
+    if (h->prof_slot[i] != slot) continue;
+    float ms = 0.f;
+    THR_CUDA(h, cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *launches = n;
   return THR_OK;
 }
 

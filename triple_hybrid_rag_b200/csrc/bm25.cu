@@ -504,9 +504,11 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   unsigned long long* keys = (unsigned long long*)ws;
   int32_t* order = (int32_t*)(ws + (size_t)B * 8);
   int* counter = (int*)(ws + (size_t)B * 8 + (((size_t)B * 4 + 15) & ~(size_t)15));
+  int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
   bm25_order_kernel<<<(B + 255) / 256, 256, 0, s>>>(keys, B, order, counter);
+  thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "bm25_order_kernel");
 
   Bm25Args a;
@@ -516,7 +518,9 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   a.out_ids = out_ids; a.out_scores = out_scores; a.out_count = out_count; a.status = h->d_status;
   THR_CUDA(h, cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBm25Smem));
   int grid = h->num_sms < B ? h->num_sms : B;
+  tok = thr_prof_begin(h, THR_PROF_BM25, s);
   bm25_kernel<<<grid, kThreads, kBm25Smem, s>>>(a);
+  thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "bm25_kernel");
   return THR_OK;
 }

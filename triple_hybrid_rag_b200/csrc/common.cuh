@@ -35,7 +35,16 @@ struct thr_handle {
   thr_bm25_state* bm25;
   void* scratch;             // generic device scratch (grown on demand)
   size_t scratch_bytes;
+  // per-kernel timing (thr_prof_*): ring of event pairs
+  int prof_on;
+  int prof_n;
+  cudaEvent_t* prof_ev;      // [2 * kProfMax]
+  unsigned char* prof_slot;  // [kProfMax]
 };
+constexpr int kProfMax = 8192;
+// Bracket a launch with events when profiling is on (no-ops otherwise).
+int thr_prof_begin(thr_handle* h, int slot, cudaStream_t s);
+void thr_prof_end(thr_handle* h, int token, cudaStream_t s);
 
 int thr_fail(thr_handle* h, int code, const char* fmt, ...);
 // Grow-only device scratch owned by the handle. Returns NULL (and sets err) on failure.

@@ -495,7 +495,9 @@ static int launch_score(thr_handle* h, const CUtensorMap& mq, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const int tok = thr_prof_begin(h, THR_PROF_DENSE_SCORE, stream);
   THR_CUDA(h, cudaLaunchKernelEx(&cfg, dense_score_kernel<G>, mq, mx, a));
+  thr_prof_end(h, tok, stream);
   h->launches++;
   return THR_OK;
 }
@@ -561,7 +563,9 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64
   f.out_count = out_count; f.out_gap = out_gap;
   const size_t fsmem = (size_t)n_clusters * f.ksel * sizeof(uint64_t) + (size_t)st->D * 2;
   THR_CUDA(h, cudaFuncSetAttribute(dense_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  const int tok = thr_prof_begin(h, THR_PROF_DENSE_FINALIZE, s);
   dense_finalize_kernel<<<B, kFinalThreads, fsmem, s>>>(f);
+  thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "dense_finalize_kernel");
   return THR_OK;
 }

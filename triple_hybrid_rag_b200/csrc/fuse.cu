@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
   const double w[3] = {a.weights[q * 3 + 0], a.weights[q * 3 + 1], a.weights[q * 3 + 2]};
   for (int e = tid; e < n; e += kFuseThreads) {
     const int64_t id = e_id[e];
+    if (id < 0) continue;  // padding of a fixed-width [B,k] result (-1 past the channel's count)
     bool first = true;
     for (int j = 0; j < e; ++j)
       if (e_id[j] == id) { first = false; break; }
@@ -405,9 +406,11 @@ int thr_fuse(thr_handle* h, int variant, int tie_mode, int B, const int64_t* lex
   a.out_ids = out_ids; a.out_rrf = out_rrf; a.out_ranks = out_ranks; a.out_raw = out_raw;
   a.out_count = out_count; a.status = h->d_status;
   cudaStream_t s = (cudaStream_t)stream;
+  const int tok = thr_prof_begin(h, THR_PROF_FUSE, s);
   if (variant == THR_FUSE_RAG2) fuse_kernel<THR_FUSE_RAG2><<<B, kFuseThreads, 0, s>>>(a);
   else if (variant == THR_FUSE_LIB) fuse_kernel<THR_FUSE_LIB><<<B, kFuseThreads, 0, s>>>(a);
   else fuse_kernel<THR_FUSE_RAG1><<<B, kFuseThreads, 0, s>>>(a);
+  thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "fuse_kernel");
   return THR_OK;
 }
@@ -421,8 +424,10 @@ int thr_safety(thr_handle* h, int B, const int32_t* off, const double* rerank,
   if (B == 0) return THR_OK;
   THR_REQUIRE(h, off && rrf && keep && refused && max_score, "thr_safety: NULL argument");
   THR_REQUIRE(h, has_rerank == nullptr || rerank != nullptr, "thr_safety: has_rerank without rerank");
+  const int tok = thr_prof_begin(h, THR_PROF_SAFETY, (cudaStream_t)stream);
   safety_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, off, rerank, has_rerank, rrf, threshold,
                                                                alpha, top_k, keep, refused, max_score);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
   THR_CHECK_LAUNCH(h, "safety_kernel");
   return THR_OK;
 }
@@ -438,8 +443,10 @@ int thr_merge_topk(thr_handle* h, const double* scores, const int64_t* ids, cons
               (long long)G * k_in, kMergeMax);
   THR_REQUIRE(h, k_out <= 256, "thr_merge_topk: k_out > 256");
   THR_REQUIRE(h, scores && ids && out_scores && out_ids && out_count, "thr_merge_topk: NULL argument");
+  const int tok = thr_prof_begin(h, THR_PROF_MERGE, (cudaStream_t)stream);
   merge_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, ids, counts, G, B, k_in, k_out, out_scores,
                                                     out_ids, out_count);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
   THR_CHECK_LAUNCH(h, "merge_kernel");
   return THR_OK;
 }

@@ -220,7 +220,9 @@ int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int
   const int units = B * a.slices;
   THR_CUDA(h, cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemM));
   int grid = units < h->num_sms ? units : h->num_sms;
+  const int tok = thr_prof_begin(h, THR_PROF_MAXSIM, (cudaStream_t)stream);
   maxsim_kernel<<<grid, kThreadsM, kSmemM, (cudaStream_t)stream>>>(map_q, map_d, a);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
   THR_CHECK_LAUNCH(h, "maxsim_kernel");
   return THR_OK;
 }

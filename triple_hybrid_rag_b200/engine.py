@@ -62,6 +62,23 @@ class Engine:
     def launches(self) -> int:
         return int(self._lib.thr_launch_count(self._h))
 
+    def prof_enable(self, on: bool = True):
+        self._check(self._lib.thr_prof_enable(self._h, int(on)))
+        self._check(self._lib.thr_prof_reset(self._h))
+
+    def prof_read(self) -> dict:
+        """{kernel: (total_ms, launches)} since prof_enable/prof_reset; synchronises the device."""
+        out = {}
+        for i, name in enumerate(_lib.PROF_SLOTS):
+            ms, n = C.c_double(), C.c_int64()
+            self._check(self._lib.thr_prof_read(self._h, i, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[name] = (ms.value, n.value)
+        return out
+
+    def prof_reset(self):
+        self._check(self._lib.thr_prof_reset(self._h))
+
     def _dev(self, t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
         if not isinstance(t, torch.Tensor):
             raise TypeError(f"{name}: expected a torch.Tensor")

@@ -1,0 +1,153 @@
+"""Batched triple-hybrid search over a resident, optionally sharded, index.
+
+This is the batch entry the reference lacks (its retriever is one query per call,
+src/voice_agent/rag2/retrieval.py:118-201); GpuRAG2Retriever (retriever.py) wraps it behind the
+reference's call surface.  Per batch:
+
+    dense top-k  (K1)  ┐
+    BM25  top-k  (K2)  ┴─ [sharded: all-gather of (score, id, count) over NCCL + K5 merge] ─┐
+    graph ranked list (input: the graph channel stays external)                             ├─ K3 fuse
+                                                                                            ┘
+
+Sharding: the corpus is cut by contiguous chunk-id range, one shard per rank;
+queries are replicated; idf / avgdl are global so shard scores equal unsharded scores; the only
+exchange is one all-gather of B x k (score, id) pairs per channel, after which every rank holds the
+merged lists and runs the fusion redundantly (no second exchange).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .engine import Engine
+from .index import BM25Index
+
+
+@dataclass
+class SearchOutput:
+    ids: torch.Tensor        # [B, top_k] int64, -1 padded
+    rrf: torch.Tensor        # [B, top_k] float64
+    ranks: torch.Tensor      # [B, top_k, 3] int32 (lexical, semantic, graph), 0 = absent
+    count: torch.Tensor      # [B] int32
+    sem_ids: torch.Tensor    # [B, k_sem] merged semantic channel
+    sem_scores: torch.Tensor
+    lex_ids: torch.Tensor    # [B, k_lex] merged lexical channel
+    lex_scores: torch.Tensor
+    lex_count: torch.Tensor
+    gap: Optional[torch.Tensor] = None  # dense exactness certificate (local shard)
+
+
+class TripleHybridSearcher:
+    def __init__(self, engine: Engine, group=None):
+        """group: a torch.distributed process group (NCCL) when the corpus is sharded, else None."""
+        self.engine = engine
+        self.group = group
+        self.world = 1
+        self.rank = 0
+        if group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+        self.has_dense = False
+        self.has_bm25 = False
+        self._pinned = {}
+        self._offs = {}
+
+    # ---- index residency -------------------------------------------------------------------
+    def set_dense(self, X_local: torch.Tensor, id_base: int = 0):
+        self.engine.dense_index_set(X_local, id_base=id_base)
+        self.has_dense = True
+
+    def set_bm25(self, index: BM25Index, id_base: int = 0):
+        d = index.to(self.engine.device)
+        self.bm25 = d
+        self.engine.bm25_index_set(d.blk_ptr, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
+        self.has_bm25 = True
+
+    # ---- one batch, device tensors in / out ------------------------------------------------
+    def search(self, Q: torch.Tensor, q_terms: torch.Tensor, q_off: torch.Tensor,
+               graph_ids: Optional[torch.Tensor], weights: Optional[torch.Tensor] = None,
+               k_sem: int = 100, k_lex: int = 100, top_k: int = 100, margin: int = 28,
+               tie_mode: int = _lib.TIE_CHUNK_ID, rrf_k: int = 60) -> SearchOutput:
+        eng, dev = self.engine, self.engine.device
+        B = Q.shape[0]
+        d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin)
+        l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex)
+        if self.world > 1:
+            d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt = self._exchange(B, k_sem, k_lex, d_ids, d_sc, d_cnt,
+                                                                    l_ids, l_sc, l_cnt)
+        if weights is None:
+            weights = self._offs.get(("w", B))
+            if weights is None:
+                weights = torch.tensor([0.7, 0.8, 1.0], dtype=torch.float64, device=dev).expand(B, 3).contiguous()
+                self._offs[("w", B)] = weights
+        # channel lists in CSR form; a fixed-width [B,k] result with a count is CSR with stride k
+        lex_list = self._as_csr(l_ids, l_cnt)
+        sem_list = self._as_csr(d_ids, d_cnt)
+        gr_list = None
+        if graph_ids is not None:
+            gr_list = self._as_csr(graph_ids, None)
+        ids, rrf, ranks, _, cnt = eng.fuse(_lib.FUSE_RAG2, B, [lex_list, sem_list, gr_list], weights, rrf_k=rrf_k,
+                                           top_k=top_k, max_out=top_k, tie_mode=tie_mode)
+        return SearchOutput(ids, rrf, ranks, cnt, d_ids, d_sc, l_ids, l_sc, l_cnt, gap)
+
+    def _as_csr(self, ids: torch.Tensor, cnt: torch.Tensor):
+        """A fixed-width [B,k] result is already CSR with stride k: thr_fuse skips the -1 padding."""
+        B, k = ids.shape
+        key = (B, k)
+        off = self._offs.get(key)
+        if off is None:
+            off = torch.arange(0, (B + 1) * k, k, dtype=torch.int32, device=ids.device)
+            self._offs[key] = off
+        return (ids.reshape(-1), off, None)
+
+    def _exchange(self, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt):
+        import torch.distributed as dist
+        eng, dev, G = self.engine, self.engine.device, self.world
+        k = max(k_sem, k_lex)
+        sc = torch.full((2, B, k), float("-inf"), dtype=torch.float64, device=dev)
+        ids = torch.full((2, B, k), -1, dtype=torch.int64, device=dev)
+        sc[0, :, :k_sem] = d_sc
+        sc[1, :, :k_lex] = l_sc.to(torch.float64)
+        ids[0, :, :k_sem] = d_ids
+        ids[1, :, :k_lex] = l_ids
+        cnt = torch.stack([d_cnt, l_cnt]).contiguous()
+        g_sc = torch.empty((G, 2 * B, k), dtype=torch.float64, device=dev)
+        g_ids = torch.empty((G, 2 * B, k), dtype=torch.int64, device=dev)
+        g_cnt = torch.empty((G, 2 * B), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(g_sc, sc.view(2 * B, k), group=self.group)
+        dist.all_gather_into_tensor(g_ids, ids.view(2 * B, k), group=self.group)
+        dist.all_gather_into_tensor(g_cnt, cnt.view(2 * B), group=self.group)
+        m_sc, m_ids, m_cnt = eng.merge_topk(g_sc, g_ids, g_cnt, k)  # dense rows then lexical rows
+        return (m_ids[:B, :k_sem].contiguous(), m_sc[:B, :k_sem].contiguous(), m_cnt[:B].clamp(max=k_sem),
+                m_ids[B:, :k_lex].contiguous(), m_sc[B:, :k_lex].to(torch.float32).contiguous(),
+                m_cnt[B:].clamp(max=k_lex))
+
+    # ---- one batch, HOST tensors in / out (the end-to-end path) ----------------------------
+    def _pin(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+            self._pinned[name] = buf
+        return buf
+
+    def search_host(self, Q: torch.Tensor, q_terms: torch.Tensor, q_off: torch.Tensor,
+                    graph_ids: Optional[torch.Tensor], **kw):
+        """Inputs are pinned CPU tensors; results come back as pinned CPU tensors.  Every call copies
+        the inputs host->device and the fused result device->host on the current stream and waits
+        for it.  Returns (ids, rrf, count, h2d_bytes, d2h_bytes)."""
+        dev = self.engine.device
+        ins = [Q, q_terms, q_off] + ([graph_ids] if graph_ids is not None else [])
+        dv = [t.to(dev, non_blocking=True) for t in ins]
+        out = self.search(dv[0], dv[1], dv[2], dv[3] if graph_ids is not None else None, **kw)
+        h_ids, h_rrf, h_cnt = self._pin("ids", out.ids), self._pin("rrf", out.rrf), self._pin("cnt", out.count)
+        h_ids.copy_(out.ids, non_blocking=True)
+        h_rrf.copy_(out.rrf, non_blocking=True)
+        h_cnt.copy_(out.count, non_blocking=True)
+        self.engine.sync()
+        h2d = sum(t.numel() * t.element_size() for t in ins)
+        d2h = sum(t.numel() * t.element_size() for t in (h_ids, h_rrf, h_cnt))
+        return h_ids, h_rrf, h_cnt, h2d, d2h

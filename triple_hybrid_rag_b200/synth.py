@@ -21,26 +21,40 @@ def _gen(device, seed: int) -> torch.Generator:
     return g
 
 
-def dense_block(block: int, rows: int, D: int, device="cpu", chunk: int = 131072) -> torch.Tensor:
-    """Rows [block*DENSE_BLOCK_ROWS, +rows) of the corpus: unit-norm Gaussian rows, bf16."""
-    g = _gen(device, 1234 + block)
-    out = torch.empty((rows, D), dtype=torch.bfloat16, device=device)
-    for s in range(0, rows, chunk):
-        n = min(chunk, rows - s)
-        x = torch.randn((n, D), generator=g, dtype=torch.float32, device=device)
+DENSE_SUB_ROWS = 131_072  # generator granularity: any aligned range can be produced independently
+
+
+def dense_rows(lo: int, hi: int, D: int, device="cpu") -> torch.Tensor:
+    """Corpus rows [lo, hi): unit-norm Gaussian rows rounded to bf16.  Sub-block s (rows
+    [s*DENSE_SUB_ROWS, +DENSE_SUB_ROWS)) is drawn from its own generator seeded 1234 + s, so a shard
+    is the same whatever the GPU count."""
+    out = torch.empty((hi - lo, D), dtype=torch.bfloat16, device=device)
+    s0, s1 = lo // DENSE_SUB_ROWS, (hi - 1) // DENSE_SUB_ROWS
+    for sb in range(s0, s1 + 1):
+        base = sb * DENSE_SUB_ROWS
+        a, b = max(lo, base), min(hi, base + DENSE_SUB_ROWS)
+        g = _gen(device, 1234 + sb)
+        x = torch.randn((b - base, D), generator=g, dtype=torch.float32, device=device)  # stream prefix
+        x = x[a - base:]
         x = x / x.norm(dim=1, keepdim=True)
-        out[s:s + n] = x.to(torch.bfloat16)
+        out[a - lo:b - lo] = x.to(torch.bfloat16)
     return out
 
 
-def dense_queries(B: int, D: int, X: torch.Tensor, noise: float = 0.5) -> torch.Tensor:
-    """Half random unit vectors, half planted near corpus rows (clear top-1, realistic spread)."""
+def dense_block(block: int, rows: int, D: int, device="cpu") -> torch.Tensor:
+    """Rows [block*DENSE_BLOCK_ROWS, +rows) of the corpus."""
+    return dense_rows(block * DENSE_BLOCK_ROWS, block * DENSE_BLOCK_ROWS + rows, D, device)
+
+
+def dense_queries(B: int, D: int, X: torch.Tensor, noise: float = 0.5, n_plant: int = 0) -> torch.Tensor:
+    """Half random unit vectors, half planted: normalize(X[j] + noise * unit_random), j < n_plant
+    (default: all of X) — gives a clear top-1 and a realistic score spread."""
     dev = X.device
     g = _gen(dev, 4321)
     q = torch.randn((B, D), generator=g, dtype=torch.float32, device=dev)
     gj = _gen("cpu", 4322)
-    j = torch.randint(0, X.shape[0], (B,), generator=gj).to(dev)
-    planted = X[j].float() + noise * q / (D ** 0.5) * (D ** 0.5) / q.norm(dim=1, keepdim=True)
+    j = torch.randint(0, n_plant or X.shape[0], (B,), generator=gj).to(dev)
+    planted = X[j].float() + noise * q / q.norm(dim=1, keepdim=True)
     use = (torch.arange(B, device=dev) % 2 == 1).unsqueeze(1)
     q = torch.where(use, planted, q)
     q = q / q.norm(dim=1, keepdim=True)
