@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 rc=0
 for f in tests/test_gpu_fuse.py tests/test_gpu_bm25.py tests/test_gpu_maxsim.py tests/test_gpu_dense.py "$@"; do
   n=$(basename $f .py)
-  timeout 900 python -m pytest $f -q -m gpu -p no:cacheprovider > gpurun_out/$n.log 2>&1
+  timeout 600 python -m pytest $f -q -m gpu -p no:cacheprovider --timeout 120 > gpurun_out/$n.log 2>&1
   r=$?
   echo "== $f exit $r"; tail -25 gpurun_out/$n.log
   [ $r -ne 0 ] && rc=1

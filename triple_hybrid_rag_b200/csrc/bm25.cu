@@ -13,9 +13,13 @@
 // Warp 16 is the producer: for every range it looks up the query terms' posting segments
 // (blk_ptr), and moves them global -> shared with cp.async.bulk into a 3-stage ring, completion on
 // an mbarrier.  Warps 0-15 consume: per term a coalesced pass shared -> accumulator (doc ids are
-// unique inside a posting list, terms are separated by a named barrier => no atomics), then one
-// scan of the accumulators that appends scores above the running threshold to a candidate list
-// (compacted by a block radix select when it fills) and re-zeroes them.
+// unique inside a posting list, terms are separated by a named barrier => no atomics).  The posting
+// that touches an accumulator first marks itself as the doc's owner (bit 31 of the staged doc id);
+// a second pass over the staged postings lets every owner read its doc's final score, append it to
+// the candidate list if it beats the running threshold (warp-aggregated) and re-zero the slot — so
+// the work per range is proportional to its postings, not to blk_docs.  Ranges too large for one
+// ring stage fall back to a scan of all accumulators.  The candidate list is compacted to the best k
+// by a block radix select when it fills; that also raises the threshold.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -29,11 +33,16 @@ constexpr int kThreads = kConsumers + 32;        // + producer warp
 constexpr int kMaxBlkDocs = 16384;
 constexpr int kStageCap = 4096;                  // postings per ring stage (32 KB)
 constexpr int kStages = 3;
-constexpr int kCandCap = 4096;
+constexpr int kCandCap = 4608;                   // >= kStageCap + kMaxSelB (one sparse pass can append a whole stage)
 constexpr int kMaxSelB = 256;
 constexpr int kScanChunk = 2048;                 // accumulator slots scanned between capacity checks
 
 struct Posting { uint32_t doc; float imp; };
+
+// A work unit: one query restricted to the doc ranges [r0, r1).  Heavy queries are cut into several
+// units so that no CTA is left streaming one long query while the others idle.
+struct Unit { int q; int r0; int r1; unsigned cost; };
+constexpr int kMaxUnitsPerQuery = 16;
 
 struct StageMeta {
   int nseg;
@@ -41,6 +50,8 @@ struct StageMeta {
   int range;             // range index
   int range_add_bound;   // upper bound of docs this range can append (valid on last step)
   int end_of_query;      // no data: consumers finish the query
+  int single;            // this step holds ALL postings of the range -> sparse second pass
+  int used;              // postings in this step (sum of seg_count)
   int seg_term[kMaxTerms + 2];    // query term slot
   int seg_start[kMaxTerms + 2];   // first valid posting inside the stage buffer
   int seg_count[kMaxTerms + 2];
@@ -57,12 +68,13 @@ struct Bm25Args {
   int64_t id_base;
   const int32_t* q_terms;
   const int32_t* q_off;
-  const int32_t* order;   // queries, heaviest first
+  const int32_t* order;   // work units, heaviest first
+  const Unit* units;
+  const int* total_units;
   int* work_counter;
   int B, k;
-  int64_t* out_ids;
-  float* out_scores;
-  int32_t* out_count;
+  uint64_t* part_keys;    // [max_units][k] sorted descending
+  int32_t* part_cnt;      // [max_units]
   thr_dev_status* status;
 };
 
@@ -161,11 +173,13 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
     __syncthreads();
     if (tid == 0) {
       int w = atomicAdd(a.work_counter, 1);
-      s_int[3] = w < a.B ? a.order[w] : -1;
+      s_int[3] = w < *a.total_units ? a.order[w] : -1;
     }
     __syncthreads();
-    const int q = s_int[3];
-    if (q < 0) break;
+    const int unit = s_int[3];
+    if (unit < 0) break;
+    const int q = a.units[unit].q;
+    const int r_begin = a.units[unit].r0, r_end = a.units[unit].r1;
     if (tid < kMaxTerms) {
       const int lo = a.q_off[q], hi = a.q_off[q + 1];
       int nt = hi - lo;
@@ -186,13 +200,22 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
     if (warp == kConsumerWarps) {
       // ======================= producer warp =======================
       const int my_term = lane < nterms ? q_term[lane] : -1;
-      for (int r = 0; r < a.n_blk; ++r) {
-        int64_t lo = 0, hi = 0;
-        if (my_term >= 0) {
+      // pointer pipeline: the (lo, hi) pair of range r + 4 is requested while range r is packed
+      auto load_ptr = [&](int r, int64_t& lo, int64_t& hi) {
+        lo = 0; hi = 0;
+        if (my_term >= 0 && r < r_end) {
           const int64_t* p = a.blk_ptr + (size_t)r * (a.V + 1) + my_term;
           lo = __ldg(p);
           hi = __ldg(p + 1);
         }
+      };
+      int64_t l0, h0, l1, h1, l2, h2, l3, h3;
+      load_ptr(r_begin, l0, h0); load_ptr(r_begin + 1, l1, h1); load_ptr(r_begin + 2, l2, h2);
+      load_ptr(r_begin + 3, l3, h3);
+      for (int r = r_begin; r < r_end; ++r) {
+        int64_t lo = l0, hi = h0;
+        l0 = l1; h0 = h1; l1 = l2; h1 = h2; l2 = l3; h2 = h3;
+        load_ptr(r + 4, l3, h3);
         int64_t remaining = hi - lo;
         // upper bound on distinct docs this range can contribute
         long long tot = remaining;
@@ -200,20 +223,62 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
         for (int s = 16; s > 0; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
         const int add_bound = (int)min((long long)R, tot);
         if (tot == 0) continue;  // nothing in this range for this query
+        bool first_step = true;
+        {
+          // Fast path (the common case): the whole range fits in one ring stage.  Lanes pack their
+          // segments with one warp scan and every lane issues its own bulk copy — no serial loop.
+          const int cnt_l = (int)remaining;
+          const int slack_l = (int)(lo & 1);
+          const int cp_l = cnt_l > 0 ? ((slack_l + cnt_l + 1) & ~1) : 0;  // postings copied (16 B granules)
+          int incl = cp_l;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+          }
+          const int total_cp = __shfl_sync(0xffffffffu, incl, 31);
+          if (total_cp <= kStageCap) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u, a.status, 402);
+            const unsigned have = __ballot_sync(0xffffffffu, cnt_l > 0);
+            const int used_before = incl - cp_l;
+            if (cnt_l > 0) {
+              const int g = __popc(have & ((1u << lane) - 1));
+              meta[s].seg_term[g] = lane;
+              meta[s].seg_start[g] = used_before + slack_l;
+              meta[s].seg_count[g] = cnt_l;
+            }
+            __syncwarp();
+            if (lane == 0) {
+              meta[s].nseg = __popc(have);
+              meta[s].last_of_range = 1;
+              meta[s].range = r;
+              meta[s].range_add_bound = add_bound;
+              meta[s].end_of_query = 0;
+              meta[s].single = 1;
+              meta[s].used = (int)tot;
+              mbar_arrive_expect_tx(full_bar(s), (uint32_t)total_cp * 8u);
+            }
+            __syncwarp();
+            if (cnt_l > 0)
+              bulk_g2s(smem_u32(stage_buf + (size_t)s * kStageCap + used_before), a.post + (lo - slack_l),
+                       (uint32_t)cp_l * 8u, full_bar(s));
+            ++it;
+            continue;
+          }
+        }
         // emit steps until every lane's segment is drained (terms in order)
-        int cur = 0;  // first term slot with data left
         while (true) {
-          // find the first lane with remaining > 0
           unsigned live = __ballot_sync(0xffffffffu, remaining > 0);
           if (!live) break;
-          cur = __ffs(live) - 1;
+          const int cur = __ffs(live) - 1;
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
-          bool okw = mbar_wait(empty_bar(s), ph ^ 1u, a.status, 400);
-          if (!__all_sync(0xffffffffu, okw)) return;
+          mbar_wait(empty_bar(s), ph ^ 1u, a.status, 400);
           // greedy packing in term order; each segment is copied from its 16-byte-aligned start
           int used = 0;  // postings used in the stage (including alignment slack)
-          int nseg = 0;
+          int nseg = 0, npost = 0;
           uint32_t bytes_total = 0;
           for (int t = cur; t < nterms; ++t) {
             int64_t rem_t = __shfl_sync(0xffffffffu, remaining, t);
@@ -239,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
             }
             bytes_total += (uint32_t)cp_postings * 8u;
             used += cp_postings;
+            npost += take;
             ++nseg;
             if (take < rem_t) break;  // stage full in the middle of this term
           }
@@ -249,9 +315,12 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
             meta[s].range = r;
             meta[s].range_add_bound = add_bound;
             meta[s].end_of_query = 0;
+            meta[s].single = (first_step && !still) ? 1 : 0;
+            meta[s].used = npost;
             // metadata is written with generic stores; the arrive has release semantics
             mbar_arrive_expect_tx(full_bar(s), bytes_total);
           }
+          first_step = false;
           ++it;
           __syncwarp();
         }
@@ -260,12 +329,13 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
-        bool okw = mbar_wait(empty_bar(s), ph ^ 1u, a.status, 401);
-        if (!__all_sync(0xffffffffu, okw)) return;
+        mbar_wait(empty_bar(s), ph ^ 1u, a.status, 401);
         if (lane == 0) {
           meta[s].nseg = 0;
           meta[s].last_of_range = 0;
           meta[s].end_of_query = 1;
+          meta[s].single = 0;
+          meta[s].used = 0;
           mbar_arrive(full_bar(s));
         }
         ++it;
@@ -277,17 +347,19 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       for (;;) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
-        bool okw = mbar_wait(full_bar(s), ph, a.status, 410);
-        if (!__all_sync(0xffffffffu, okw)) return;
+        mbar_wait(full_bar(s), ph, a.status, 410);
         ++it;
         const StageMeta& m = meta[s];
         const int nseg = m.nseg;
         const bool eoq = m.end_of_query != 0;
         const bool last = m.last_of_range != 0;
+        const bool single = m.single != 0;
+        const int used = m.used;
         const int r = m.range;
         const int add_bound = m.range_add_bound;
-        const Posting* sb = stage_buf + (size_t)s * kStageCap;
+        Posting* sb = stage_buf + (size_t)s * kStageCap;
         const uint32_t doc0 = (uint32_t)r * (uint32_t)R;
+        // ---- pass 1: accumulate, term by term ----
         int prev_term = -1;
         for (int g = 0; g < nseg; ++g) {
           const int t = m.seg_term[g];
@@ -299,17 +371,63 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
           for (int i = tid; i < cn; i += kConsumers) {
             const Posting p = sb[st + i];
             const uint32_t slot = p.doc - doc0;
-            acc[slot] = __fadd_rn(acc[slot], __fmul_rn(w, p.imp));
+            const float old = acc[slot];
+            acc[slot] = __fadd_rn(old, __fmul_rn(w, p.imp));
+            if (single && old == 0.f) sb[st + i].doc = p.doc | 0x80000000u;  // first touch owns the doc
           }
         }
-        // this stage's shared buffer is free once every consumer warp has read it
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(s));
+        if (!single) {
+          // this stage's shared buffer is free once every consumer warp has read it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(s));
+        }
         if (eoq) break;
-        if (nseg > 0) bar_consumers();  // all accumulates of this step done (next step may hit same docs)
+        if (nseg > 0) bar_consumers();  // all accumulates of this step done
+
+        if (single) {
+          // ---- pass 2 (sparse): owners read the final score, append if > tau, re-zero ----
+          int cnt_now = s_int[2];
+          if (cnt_now + used > kCandCap) {  // block-uniform; implies cnt_now > kMaxSelB >= k
+            const uint64_t T = block_compact_topk(cand, cnt_now, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
+            tau = key_score(T);
+            if (tid == 0) s_int[2] = s_int[1];
+            bar_consumers();
+          }
+          for (int g = 0; g < nseg; ++g) {
+            const int st = m.seg_start[g];
+            const int cn = m.seg_count[g];
+            for (int i0 = warp * 32; i0 < cn; i0 += kConsumers) {
+              const int i = i0 + lane;
+              bool emit = false;
+              uint64_t key = 0;
+              if (i < cn) {
+                const uint32_t d = sb[st + i].doc;
+                if (d & 0x80000000u) {
+                  const uint32_t doc = d & 0x7fffffffu;
+                  const uint32_t slot = doc - doc0;
+                  const float v = acc[slot];
+                  acc[slot] = 0.f;
+                  emit = v > tau;
+                  key = pack_key(v, doc);
+                }
+              }
+              const unsigned bal = __ballot_sync(0xffffffffu, emit);
+              if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_int[2], __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (emit) cand[base + __popc(bal & ((1u << lane) - 1))] = key;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(s));
+          bar_consumers();  // slots re-zeroed and appends visible before the next range
+          continue;
+        }
         if (!last) continue;
 
-        // ---- scan the range: append score > tau, re-zero ----
+        // ---- fallback for ranges spread over several steps: scan all accumulators ----
         const int ndocs_r = (int)min((int64_t)R, a.n_docs - (int64_t)r * R);
         int cnt_now = s_int[2];
         const bool tight = cnt_now + add_bound > kCandCap;  // block-uniform
@@ -318,8 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
             bar_consumers();
             cnt_now = s_int[2];
             if (cnt_now + kScanChunk > kCandCap) {
-              const uint64_t T = block_compact_topk(cand, cnt_now, min(a.k, kMaxSelB), hist, s_prefix,
-                                                    &s_int[0], &s_int[1], tid);
+              const uint64_t T = block_compact_topk(cand, cnt_now, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
               tau = key_score(T);
               if (tid == 0) s_int[2] = s_int[1];
               bar_consumers();
@@ -343,15 +460,6 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
           }
         }
         bar_consumers();  // scan complete before the next range accumulates
-        // keep headroom so that the common (non-tight) path never overflows
-        cnt_now = s_int[2];
-        if (cnt_now > kCandCap / 2 && cnt_now > a.k) {
-          const uint64_t T = block_compact_topk(cand, cnt_now, min(a.k, kMaxSelB), hist, s_prefix,
-                                                &s_int[0], &s_int[1], tid);
-          tau = key_score(T);
-          if (tid == 0) s_int[2] = s_int[1];
-          bar_consumers();
-        }
       }
 
       // ---- end of query: final top-k, sorted ----
@@ -378,22 +486,13 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
           bar_consumers();
         }
       }
-      if (tid == 0) a.out_count[q] = n;
-      for (int i = tid; i < a.k; i += kConsumers) {
-        size_t o = (size_t)q * a.k + i;
-        if (i < n) {
-          a.out_ids[o] = a.id_base + (int64_t)key_index(cand[i]);
-          a.out_scores[o] = key_score(cand[i]);
-        } else {
-          a.out_ids[o] = -1;
-          a.out_scores[o] = 0.f;
-        }
-      }
+      if (tid == 0) a.part_cnt[unit] = n;
+      for (int i = tid; i < n; i += kConsumers) a.part_keys[(size_t)unit * a.k + i] = cand[i];
     }
   }
 }
 
-// cost[q] = total postings of the query's terms; order = queries sorted by cost descending.
+// cost[q] = total postings of the query's terms.
 __global__ void bm25_df_kernel(const int64_t* blk_ptr, int n_blk, int V, int64_t* df) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V) return;
@@ -418,14 +517,119 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
   keys[q] = ((unsigned long long)c << 32) | (unsigned)(0xffffffffu - (unsigned)q);
 }
 
-// Single-block rank sort: order[rank] = q.  B is small (<= a few thousand).
-__global__ void bm25_order_kernel(const unsigned long long* keys, int B, int32_t* order, int* work_counter) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *work_counter = 0;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < B; q += gridDim.x * blockDim.x) {
-    unsigned long long kq = keys[q];
+// Single block: cut queries into units of roughly equal posting count.
+__global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
+                                                          int num_sms, Unit* units, int* unit_base,
+                                                          int* total_units, int* work_counter) {
+  __shared__ unsigned long long s_tot;
+  __shared__ int s_carry;
+  __shared__ int s_scan[1024];
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_tot = 0; s_carry = 0; *work_counter = 0; }
+  __syncthreads();
+  unsigned long long part = 0;
+  for (int q = tid; q < B; q += 1024) part += keys[q] >> 32;
+  atomicAdd(&s_tot, part);
+  __syncthreads();
+  unsigned long long target = s_tot / (unsigned long long)(num_sms * 2) + 1;
+  if (target < 32768ull) target = 32768ull;
+  for (int q0 = 0; q0 < B; q0 += 1024) {
+    const int q = q0 + tid;
+    int nu = 0;
+    unsigned long long c = 0;
+    if (q < B) {
+      c = keys[q] >> 32;
+      nu = (int)((c + target - 1) / target);
+      if (nu < 1) nu = 1;
+      if (nu > kMaxUnitsPerQuery) nu = kMaxUnitsPerQuery;
+      if (nu > n_blk) nu = n_blk;
+    }
+    s_scan[tid] = nu;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan
+      int v = tid >= off ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const int base = s_carry + s_scan[tid] - nu;
+    if (q < B) {
+      unit_base[q] = base;
+      for (int u = 0; u < nu; ++u) {
+        Unit x;
+        x.q = q;
+        x.r0 = (int)((long long)n_blk * u / nu);
+        x.r1 = (int)((long long)n_blk * (u + 1) / nu);
+        x.cost = (unsigned)min(c / (unsigned long long)nu, 0xffffffffull);
+        units[base + u] = x;
+      }
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry += s_scan[1023];
+    __syncthreads();
+  }
+  if (tid == 0) { unit_base[B] = s_carry; *total_units = s_carry; }
+}
+
+// Rank sort of the units by cost, heaviest first (n <= B * kMaxUnitsPerQuery, a few thousand).
+__global__ void bm25_order_kernel(const Unit* units, const int* total_units, int32_t* order) {
+  const int n = *total_units;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const unsigned cu = units[u].cost;
     int rank = 0;
-    for (int j = 0; j < B; ++j) rank += keys[j] > kq ? 1 : 0;
-    order[rank] = q;
+    for (int j = 0; j < n; ++j) {
+      const unsigned cj = units[j].cost;
+      rank += (cj > cu || (cj == cu && j < u)) ? 1 : 0;
+    }
+    order[rank] = u;
+  }
+}
+
+// Per query: merge the sorted partial lists of its units -> final top-k.
+__global__ void __launch_bounds__(256) bm25_merge_kernel(const uint64_t* part_keys, const int32_t* part_cnt,
+                                                         const int* unit_base, int k, int64_t id_base,
+                                                         int64_t* out_ids, float* out_scores, int32_t* out_count) {
+  __shared__ uint64_t keys[kMaxUnitsPerQuery * kMaxSelB];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int u0 = unit_base[q], u1 = unit_base[q + 1];
+  const int slots = (u1 - u0) * k;
+  int P = 32;
+  while (P < slots) P <<= 1;
+  for (int i = tid; i < P; i += 256) {
+    uint64_t key = 0ull;
+    if (i < slots) {
+      const int u = u0 + i / k, j = i % k;
+      if (j < part_cnt[u]) key = part_keys[(size_t)u * k + j];
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P >> 1); i += 256) {
+        int lo = ((i / stride) * (stride << 1)) + (i % stride);
+        int hi = lo + stride;
+        bool desc_block = ((lo & size) == 0);
+        uint64_t x = keys[lo], y = keys[hi];
+        bool swap = desc_block ? (y > x) : (x > y);
+        if (swap) { keys[lo] = y; keys[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  int n = 0;
+  for (int u = u0; u < u1; ++u) n += part_cnt[u];
+  if (n > k) n = k;
+  if (tid == 0) out_count[q] = n;
+  for (int i = tid; i < k; i += 256) {
+    size_t o = (size_t)q * k + i;
+    if (i < n) {
+      out_ids[o] = id_base + (int64_t)key_index(keys[i]);
+      out_scores[o] = key_score(keys[i]);
+    } else {
+      out_ids[o] = -1;
+      out_scores[o] = 0.f;
+    }
   }
 }
 
@@ -466,7 +670,7 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* blk_ptr, const void* postin
                     blk_docs, kMaxBlkDocs);
   THR_REQUIRE(h, (int64_t)n_blk * blk_docs >= n_docs && (int64_t)(n_blk - 1) * blk_docs < n_docs,
               "thr_bm25_index_set: n_blk does not match n_docs / blk_docs");
-  THR_REQUIRE(h, n_docs < ((int64_t)1 << 32), "thr_bm25_index_set: more than 2^32 docs per shard");
+  THR_REQUIRE(h, n_docs < ((int64_t)1 << 31), "thr_bm25_index_set: more than 2^31 docs per shard (bit 31 of a staged doc id is the owner flag)");
   THR_REQUIRE(h, ((uintptr_t)postings & 15u) == 0, "thr_bm25_index_set: postings must be 16-byte aligned");
   thr_bm25_state_free(h);
   thr_bm25_state* st = (thr_bm25_state*)calloc(1, sizeof(thr_bm25_state));
@@ -497,31 +701,52 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   if (B == 0) return THR_OK;
   THR_REQUIRE(h, q_terms && q_off && out_ids && out_scores && out_count, "thr_bm25_topk: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
-  // scratch: keys [B] u64 | order [B] i32 | counter
-  const size_t need = (size_t)B * 8 + (size_t)B * 4 + 64;
+  // scratch: cost keys | units | order | unit_base | counters | partial lists
+  const size_t max_units = (size_t)B * kMaxUnitsPerQuery;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_keys = 0;
+  const size_t o_units = o_keys + up((size_t)B * 8);
+  const size_t o_order = o_units + up(max_units * sizeof(Unit));
+  const size_t o_base = o_order + up(max_units * 4);
+  const size_t o_cnt = o_base + up((size_t)(B + 1) * 4);
+  const size_t o_pcnt = o_cnt + 256;
+  const size_t o_pkeys = o_pcnt + up(max_units * 4);
+  const size_t need = o_pkeys + up(max_units * (size_t)k * 8);
   uint8_t* ws = (uint8_t*)thr_scratch(h, need);
   if (!ws) return THR_ENOMEM;
-  unsigned long long* keys = (unsigned long long*)ws;
-  int32_t* order = (int32_t*)(ws + (size_t)B * 8);
-  int* counter = (int*)(ws + (size_t)B * 8 + (((size_t)B * 4 + 15) & ~(size_t)15));
+  unsigned long long* keys = (unsigned long long*)(ws + o_keys);
+  Unit* units = (Unit*)(ws + o_units);
+  int32_t* order = (int32_t*)(ws + o_order);
+  int* unit_base = (int*)(ws + o_base);
+  int* counter = (int*)(ws + o_cnt);
+  int* total_units = counter + 1;
+  int32_t* part_cnt = (int32_t*)(ws + o_pcnt);
+  uint64_t* part_keys = (uint64_t*)(ws + o_pkeys);
+
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
-  bm25_order_kernel<<<(B + 255) / 256, 256, 0, s>>>(keys, B, order, counter);
+  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, h->num_sms, units, unit_base, total_units, counter);
+  THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
+  bm25_order_kernel<<<32, 256, 0, s>>>(units, total_units, order);
   thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "bm25_order_kernel");
 
   Bm25Args a;
   a.blk_ptr = st->blk_ptr; a.post = (const Posting*)st->post; a.idf = st->idf; a.n_docs = st->n_docs;
   a.n_blk = st->n_blk; a.blk_docs = st->blk_docs; a.V = st->V; a.id_base = st->id_base;
-  a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.work_counter = counter; a.B = B; a.k = k;
-  a.out_ids = out_ids; a.out_scores = out_scores; a.out_count = out_count; a.status = h->d_status;
+  a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.units = units; a.total_units = total_units;
+  a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
+  a.status = h->d_status;
   THR_CUDA(h, cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBm25Smem));
-  int grid = h->num_sms < B ? h->num_sms : B;
   tok = thr_prof_begin(h, THR_PROF_BM25, s);
-  bm25_kernel<<<grid, kThreads, kBm25Smem, s>>>(a);
+  bm25_kernel<<<h->num_sms, kThreads, kBm25Smem, s>>>(a);
   thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "bm25_kernel");
+  tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
+  bm25_merge_kernel<<<B, 256, 0, s>>>(part_keys, part_cnt, unit_base, k, st->id_base, out_ids, out_scores, out_count);
+  thr_prof_end(h, tok, s);
+  THR_CHECK_LAUNCH(h, "bm25_merge_kernel");
   return THR_OK;
 }
 

@@ -167,9 +167,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Arrive on a barrier that lives in another CTA of the cluster (address from mapa_u32).
+// Default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive: the barriers this
+// is used for order TMEM accesses, which the tcgen05 fences cover; a cluster-scope release would
+// compile to MEMBAR.ALL.GPU and wait for every outstanding candidate store.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;

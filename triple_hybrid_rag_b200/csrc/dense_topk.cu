@@ -32,13 +32,13 @@ constexpr int kBlockK = 64;        // bf16 elements per k-block = one 128-byte s
 constexpr int kUmmaK = 16;
 constexpr int kAccStages = 2;      // 2 x 256 TMEM columns
 constexpr int kTmemCols = 512;
-constexpr int kCap = 512;          // candidate slots per (cluster, query)
+constexpr int kCap = 1024;         // candidate slots per (cluster, query); raw keys {~idx, score bits}
 constexpr int kMaxSel = 256;       // largest K' = k + margin
 constexpr int kScoreThreads = 192;
 constexpr int kFinalThreads = 256;
 
 template <int G> struct ScoreCfg {
-  static constexpr int kStages = (G == 2) ? 6 : 4;
+  static constexpr int kStages = (G == 2) ? 7 : 4;
   static constexpr int kABytes = kBlockM * kBlockK * 2;                 // 16 KB
   static constexpr int kBBytes = (G == 2 ? 128 : 256) * kBlockK * 2;    // 16 / 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -58,16 +58,35 @@ struct ScoreArgs {
   thr_dev_status* status;
 };
 
+// Candidate lists hold RAW keys (fp32 score bits << 32 | ~chunk_index): the epilogue appends them with
+// three predicated instructions per score; the order-preserving transform is applied when a list is
+// read (here and in the finalize kernel).
+__device__ __forceinline__ uint64_t raw_to_orderable(uint64_t raw) {
+  return ((uint64_t)f32_orderable(__uint_as_float((uint32_t)(raw >> 32))) << 32) | (raw & 0xffffffffull);
+}
+
+// Branch-free append: if (v > tau) { *ptr++ = {inv_idx0 - col, v}; }
+#define THR_PUSH_IF(ptr, vbits, tau, inv0, col)                                               \
+  asm volatile(                                                                               \
+      "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"                                               \
+      "setp.gt.f32 p, %1, %2;\n\t"                                                            \
+      "@p sub.u32 t, %3, %4;\n\t"                                                             \
+      "@p st.global.v2.b32 [%0], {t, %5};\n\t"                                                \
+      "@p add.u64 %0, %0, 8;\n\t}"                                                            \
+      : "+l"(ptr)                                                                             \
+      : "f"(__uint_as_float(vbits)), "f"(tau), "r"(inv0), "n"(col), "r"(vbits)                \
+      : "memory")
+
 // Warp-cooperative: keep the `ksel` largest of the n (<= kCap) distinct keys in row[0..n), in place.
-// Returns the ksel-th largest key (valid in every lane).  Requires n > ksel.
+// Returns the ksel-th largest key in ORDERABLE form (valid in every lane).  Requires n > ksel.
 __device__ uint64_t warp_compact_topk(uint64_t* row, int n, int ksel, uint32_t lane) {
   constexpr int kPer = kCap / 32;
   uint32_t hi[kPer], lo[kPer];
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
     int i = lane + 32 * j;
-    uint64_t key = i < n ? row[i] : 0ull;
-    hi[j] = (uint32_t)(key >> 32);
+    uint64_t key = i < n ? row[i] : 0ull;   // raw: score bits << 32 | ~idx
+    hi[j] = i < n ? f32_orderable(__uint_as_float((uint32_t)(key >> 32))) : 0u;
     lo[j] = (uint32_t)key;
   }
   // radix descent over the 64 key bits: T = largest value with count(keys >= T) >= ksel
@@ -101,7 +120,8 @@ __device__ uint64_t warp_compact_topk(uint64_t* row, int n, int ksel, uint32_t l
     keep = keep && (int)(lane + 32 * j) < n;
     unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (keep) {
-      row[base + __popc(bal & ((1u << lane) - 1))] = ((uint64_t)hi[j] << 32) | lo[j];
+      row[base + __popc(bal & ((1u << lane) - 1))] =
+          ((uint64_t)__float_as_uint(f32_from_orderable(hi[j])) << 32) | lo[j];
       if (hi[j] < m_hi || (hi[j] == m_hi && lo[j] < m_lo)) { m_hi = hi[j]; m_lo = lo[j]; }
     }
     base += __popc(bal);
@@ -175,63 +195,72 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp == 4) {
     // ===================== TMA producer (one lane, both CTAs of a pair) =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      bool ok = true;
-      for (int qb = 0; qb < qblocks && ok; ++qb) {
+      uint32_t stage = 0, phase = 0;
+      for (int qb = 0; qb < qblocks; ++qb) {
         const int q_row = qb * qrows + (int)rank * kBlockM;
-        for (int64_t t = tile_lo; t < tile_hi && ok; ++t) {
-          const int64_t x_row = t * kTileN + (G == 2 ? (int64_t)rank * 128 : 0);
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int s = it % Cfg::kStages;
-            const uint32_t ph = (it / Cfg::kStages) & 1u;
-            if (!mbar_wait(empty_bar(s), ph ^ 1u, a.status, 100)) { ok = false; break; }
-            const uint32_t fb = (G == 2) ? mapa_u32(full_bar(s), 0) : full_bar(s);
-            if (leader) mbar_arrive_expect_tx(full_bar(s), Cfg::kTxBytes);
+        for (int64_t t = tile_lo; t < tile_hi; ++t) {
+          const int32_t x_row = (int32_t)(t * kTileN + (G == 2 ? (int64_t)rank * 128 : 0));
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, a.status, 100);
+            const uint32_t fb = (G == 2) ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kTxBytes);
             if (G == 2) {
-              tma_load_2d_pair(a_smem(s), &map_q, fb, kb * kBlockK, q_row, THR_L2_EVICT_LAST);
-              tma_load_2d_pair(b_smem(s), &map_x, fb, kb * kBlockK, (int32_t)x_row, THR_L2_EVICT_FIRST);
+              tma_load_2d_pair(a_smem(stage), &map_q, fb, kb * kBlockK, q_row, THR_L2_EVICT_LAST);
+              tma_load_2d_pair(b_smem(stage), &map_x, fb, kb * kBlockK, x_row, THR_L2_EVICT_FIRST);
             } else {
-              tma_load_2d(a_smem(s), &map_q, fb, kb * kBlockK, q_row, THR_L2_EVICT_LAST);
-              tma_load_2d(b_smem(s), &map_x, fb, kb * kBlockK, (int32_t)x_row, THR_L2_EVICT_FIRST);
-              tma_load_2d(b_smem(s) + 128 * kBlockK * 2, &map_x, fb, kb * kBlockK,
-                          (int32_t)x_row + 128, THR_L2_EVICT_FIRST);
+              tma_load_2d(a_smem(stage), &map_q, fb, kb * kBlockK, q_row, THR_L2_EVICT_LAST);
+              tma_load_2d(b_smem(stage), &map_x, fb, kb * kBlockK, x_row, THR_L2_EVICT_FIRST);
+              tma_load_2d(b_smem(stage) + 128 * kBlockK * 2, &map_x, fb, kb * kBlockK, x_row + 128,
+                          THR_L2_EVICT_FIRST);
             }
+            if (++stage == (uint32_t)Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 5) {
-    // ===================== MMA issuer (leader CTA, one lane) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA) =====================
+    // The whole warp runs the loop converged (uniform branches, uniform registers); one elected
+    // lane issues the tcgen05 instructions.  Descriptors are precomputed: stage s adds
+    // s * (stage bytes >> 4) to the 14-bit start-address field, K-step k adds 2 (32 bytes).
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM * G, kTileN);
-      uint32_t it = 0, tcount = 0;
-      bool ok = true;
-      for (int qb = 0; qb < qblocks && ok; ++qb) {
-        for (int64_t t = tile_lo; t < tile_hi && ok; ++t, ++tcount) {
-          const int acc = tcount & 1;
+      constexpr uint32_t kStageDescStep = (uint32_t)Cfg::kStageBytes >> 4;
+      const uint64_t adesc0 = umma_desc_sw128(a_smem(0));
+      const uint64_t bdesc0 = umma_desc_sw128(b_smem(0));
+      uint32_t stage = 0, phase = 0, tcount = 0;
+      for (int qb = 0; qb < qblocks; ++qb) {
+        for (int64_t t = tile_lo; t < tile_hi; ++t, ++tcount) {
+          const uint32_t acc = tcount & 1u;
           const uint32_t aph = (tcount >> 1) & 1u;
-          if (!mbar_wait_cluster(tempty_bar(acc), aph ^ 1u, a.status, 200)) { ok = false; break; }
+          mbar_wait(tempty_bar(acc), aph ^ 1u, a.status, 200);
           tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int s = it % Cfg::kStages;
-            const uint32_t ph = (it / Cfg::kStages) & 1u;
-            if (!mbar_wait(full_bar(s), ph, a.status, 201)) { ok = false; break; }
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)kTileN;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(full_bar(stage), phase, a.status, 201);
             tc_fence_after_sync();
-            const uint64_t adesc = umma_desc_sw128(a_smem(s));
-            const uint64_t bdesc = umma_desc_sw128(b_smem(s));
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // +32 bytes per K=16 step inside the 128-byte swizzle row (>>4 in the address field)
-              umma_bf16<G>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            if (lane == 0) {
+              const uint64_t adesc = adesc0 + (uint64_t)(stage * kStageDescStep);
+              const uint64_t bdesc = bdesc0 + (uint64_t)(stage * kStageDescStep);
+#ifndef THR_DBG_NO_MMA
+              umma_bf16<G>(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+              umma_bf16<G>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              umma_bf16<G>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_bf16<G>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+#else
+              (void)adesc; (void)bdesc; (void)d_tmem;
+#endif
+              if (G == 2) umma_commit_pair_mcast(empty_bar(stage), 0x3);
+              else umma_commit_1cta(empty_bar(stage));
             }
-            if (G == 2) umma_commit_pair_mcast(empty_bar(s), 0x3);
-            else umma_commit_1cta(empty_bar(s));
+            __syncwarp();
+            if (++stage == (uint32_t)Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
-          if (!ok) break;
-          if (G == 2) umma_commit_pair_mcast(tfull_bar(acc), 0x3);
-          else umma_commit_1cta(tfull_bar(acc));
+          if (lane == 0) {
+            if (G == 2) umma_commit_pair_mcast(tfull_bar(acc), 0x3);
+            else umma_commit_1cta(tfull_bar(acc));
+          }
+          __syncwarp();
         }
       }
     }
@@ -244,7 +273,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const int row = qb * qrows + (int)rank * kBlockM + (int)lane_base + (int)lane;  // query index
       const bool row_valid = row < a.B;
       uint64_t* rowbuf = a.cand + ((size_t)cluster_id * a.Bpad + (row_valid ? row : 0)) * kCap;
-      float tau = -CUDART_INF_F;
+      float tau = row_valid ? -CUDART_INF_F : CUDART_INF_F;  // padding rows of the query block never pass
       int cnt = 0;
       for (int64_t t = tile_lo; t < tile_hi && ok; ++t, ++tcount) {
         const int acc = tcount & 1;
@@ -265,23 +294,59 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tc_fence_after_sync();
         const int64_t col0 = t * kTileN;
         const int ncols = (int)min((int64_t)kTileN, a.N - col0);
+        uint64_t* wptr = rowbuf + cnt;
+#ifdef THR_DBG_NO_LDTM
+        if (ncols == kTileN + 1) {
+#else
+        if (ncols == kTileN) {
+#endif
+          // full tile
 #pragma unroll 1
-        for (int c = 0; c < kTileN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (lane_base << 16) + (uint32_t)(acc * kTileN + c * 32), r);
-          tmem_ld_wait();
-          if (row_valid) {
+          for (int c = 0; c < kTileN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (lane_base << 16) + (uint32_t)(acc * kTileN + c * 32), r);
+            tmem_ld_wait();
+#ifdef THR_DBG_NO_FILTER
+            if (r[0] == 0x7fc12345u) {  // experiment: keep the loads, drop the filter work
+#else
+            {  // all 32 lanes take part in the votes; lanes without a query row never pass (tau = +inf)
+#endif
+              const uint32_t inv0 = ~(uint32_t)(col0 + c * 32);  // ~(col0 + c*32 + j) == inv0 - j
+// Four columns at a time: max + one compare + one warp vote; the (predicated) appends run only when
+// some lane of the warp passes — after warm-up that is ~ 128*K'/seen of the groups.
+#define P1(j) if (__uint_as_float(r[j]) > tau) *wptr++ = ((uint64_t)r[j] << 32) | (uint64_t)(inv0 - (uint32_t)(j));
+#define P(j)                                                                                       \
+  {                                                                                                \
+    const float m4 = fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),                \
+                           fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));           \
+    if (__any_sync(0xffffffffu, m4 > tau)) {                                                       \
+      asm volatile("" ::: "memory"); /* keep this a real (warp-uniform) branch */                  \
+      P1(j) P1(j + 1) P1(j + 2) P1(j + 3)                                                          \
+    }                                                                                              \
+  }
+              P(0); P(4); P(8); P(12); P(16); P(20); P(24); P(28);
+#undef P1
+#undef P
+            }
+          }
+        } else if (ncols < kTileN) {
+          // last, partial tile of the corpus (zero-filled rows past N are skipped)
+#pragma unroll 1
+          for (int c = 0; c < kTileN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (lane_base << 16) + (uint32_t)(acc * kTileN + c * 32), r);
+            tmem_ld_wait();
+            if (row_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]);
-              const int col = c * 32 + j;
-              if (v > tau && col < ncols) {
-                if (cnt < kCap) rowbuf[cnt] = pack_key(v, (uint32_t)(col0 + col));
-                ++cnt;
+              for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                if (__uint_as_float(r[j]) > tau && col < ncols)
+                  *wptr++ = ((uint64_t)r[j] << 32) | (uint64_t)(~(uint32_t)(col0 + col));
               }
             }
           }
         }
+        cnt = (int)(wptr - rowbuf);
         if (cnt > kCap) {  // cannot happen given the pre-tile compaction; keep the invariant loud
           dev_report(a.status, THR_EOVERFLOW, 301, cnt);
           cnt = kCap;
@@ -359,7 +424,7 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
     int base = 0;
     if (lane == 0 && n > 0) base = atomicAdd(&s_m, n);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (int i = lane; i < n; i += 32) keys[base + i] = src[i];
+    for (int i = lane; i < n; i += 32) keys[base + i] = raw_to_orderable(src[i]);
   }
   __syncthreads();
   const int m = s_m;
