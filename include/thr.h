@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 1
+#define THR_ABI_VERSION 2
 
 enum {
   THR_OK = 0,
@@ -116,15 +116,17 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin,
  * formula is BM25 as BASELINE.json's north_star asks (Postgres ts_rank_cd is not in the
  * reference tree); it is defined in oracle/bm25.py and DESIGN.md.
  *
- * Index layout (built by triple_hybrid_rag_b200.index.BM25Index on the device):
- *   documents are split into n_blk ranges of blk_docs consecutive local doc ids;
- *   postings are ordered by (range, term, doc) and stored as 8-byte records
- *   {uint32 local_doc, float impact}, impact = tf*(k1+1)/(tf + k1*(1-b+b*len/avgdl));
- *   blk_ptr [n_blk*(V+1)] int64: postings[blk_ptr[r*(V+1)+t] .. blk_ptr[r*(V+1)+t+1])
- *   are term t's postings inside range r;  idf [V] float.
- * blk_docs must be a multiple of 1024 and <= 16384.  Arrays stay resident (not copied).
+ * Index layout (built by triple_hybrid_rag_b200.index.BM25Index on the device): a CSR inverted
+ * index with per-term range skips.
+ *   postings: 8-byte records {uint32 local_doc, float impact}, term-major, doc ascending inside a
+ *   term; impact = tf*(k1+1)/(tf + k1*(1-b+b*len/avgdl)); 16 bytes of padding after the last record.
+ *   Documents are split into n_blk ranges of blk_docs consecutive local doc ids;
+ *   skip [V*n_blk + 1] int64: postings[skip[t*n_blk + r] .. skip[t*n_blk + r + 1]) are term t's
+ *   postings inside range r (so skip[t*n_blk] .. skip[(t+1)*n_blk] is term t's whole list: the
+ *   usual CSR indptr is skip[::n_blk]);  idf [V] float.
+ * blk_docs must be a power of two in [1024, 16384].  Arrays stay resident (not copied).
  */
-int thr_bm25_index_set(thr_handle* h, const int64_t* blk_ptr, const void* postings,
+int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
                        const float* idf, int64_t n_docs, int32_t n_blk, int32_t blk_docs,
                        int32_t V, int64_t id_base);
 

@@ -15,7 +15,7 @@ for gb in range((N + G - 1) // G):
     doc, term, tf, L = synth.bm25_block_coo(gb, rows, V=V, device=dev)
     parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=16384, avgdl=200.0, n_docs_global=N))
 idx = BM25Index.concat(parts) if len(parts) > 1 else parts[0]
-eng.bm25_index_set(idx.blk_ptr, idx.postings, idx.idf, idx.n_docs, idx.blk_docs, idx.V)
+eng.bm25_index_set(idx.skip, idx.postings, idx.idf, idx.n_docs, idx.blk_docs, idx.V)
 qs = synth.bm25_queries(B, V=V)
 qt, qo = pack_queries(qs, dev)
 eng.prof_enable(True)

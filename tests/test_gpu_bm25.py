@@ -20,7 +20,7 @@ def _corpus(n_docs, V, blk_docs):
 
 def _check(engine, idx, orc, queries, k, id_base=0):
     d = idx.to(engine.device)
-    engine.bm25_index_set(d.blk_ptr, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
+    engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
     qt, qo = pack_queries(queries, engine.device)
     ids, sc, cnt = engine.bm25_topk(qt, qo, k)
     engine.sync()

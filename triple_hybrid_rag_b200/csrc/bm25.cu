@@ -1,4 +1,4 @@
-// bm25.cu — K2: BM25 top-k over a blocked CSR inverted index (lexical channel).
+// bm25.cu — K2: BM25 top-k over a CSR inverted index with per-term range skips (lexical channel).
 //
 // Stands where RAG2Retriever._lexical_search calls the rag2_lexical_search RPC
 //   (src/voice_agent/rag2/retrieval.py:273-292, database/migrations/20260114_rag2_schema.sql:341-374):
@@ -8,18 +8,26 @@
 //   with fp32 round-to-nearest multiply and add and no FMA contraction, so the result does not
 //   depend on scheduling; docs with score > 0 are ranked by (score desc, id asc).
 //
-// One CTA works on one query at a time (persistent grid, queries handed out heaviest first).
-// The doc space is walked range by range (blk_docs docs, fp32 accumulators in shared memory).
-// Warp 16 is the producer: for every range it looks up the query terms' posting segments
-// (blk_ptr), and moves them global -> shared with cp.async.bulk into a 3-stage ring, completion on
-// an mbarrier.  Warps 0-15 consume: per term a coalesced pass shared -> accumulator (doc ids are
-// unique inside a posting list, terms are separated by a named barrier => no atomics).  The posting
-// that touches an accumulator first marks itself as the doc's owner (bit 31 of the staged doc id);
-// a second pass over the staged postings lets every owner read its doc's final score, append it to
-// the candidate list if it beats the running threshold (warp-aggregated) and re-zero the slot — so
-// the work per range is proportional to its postings, not to blk_docs.  Ranges too large for one
-// ring stage fall back to a scan of all accumulators.  The candidate list is compacted to the best k
-// by a block radix select when it fills; that also raises the threshold.
+// Index (include/thr.h): postings {u32 doc, f32 impact} in term-major CSR order (doc ascending inside
+// a term) and skip[t * n_blk + r] = first posting of term t whose doc lies in range r (blk_docs docs).
+//
+// One CTA works on one unit (a query restricted to a span of doc ranges; heavy queries are cut into
+// several units) at a time, walking the span range by range with fp32 accumulators for one range in
+// shared memory.  Two warp roles, asynchronous to each other through mbarriers:
+//   producer (1 warp)  per range: reads the query terms' skip entries (prefetched 12 ranges ahead with
+//                      cp.async), packs the terms' posting segments into one step, allocates room in a
+//                      96 KB ring and moves the segments global -> shared with cp.async.bulk.
+//   consumers          per step, term by term: one coalesced pass shared -> accumulator (doc ids are
+//                      unique inside a posting list and terms are separated by a named barrier => no
+//                      atomics).  The posting that touches an accumulator first marks itself as the
+//                      doc's owner (bit 31 of the staged doc id); one more pass over the staged postings
+//                      lets every owner read its doc's final score, append it to the candidate list if
+//                      it beats the running threshold and re-zero the slot, so the work per range is
+//                      proportional to its postings, not to blk_docs.  A range too large for one step
+//                      falls back to a scan of the accumulators.
+// The barrier after a range's last term doubles as the capacity vote (bar.red.or): when the candidate
+// list could overflow it is compacted to the best k by a radix select, which also raises the threshold.
+// The per-step code is kept to ~150 instructions per thread: the kernel is issue-bound, not DRAM-bound.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -27,45 +35,46 @@
 namespace {
 
 constexpr int kMaxTerms = 32;
-constexpr int kConsumerWarps = 16;
-constexpr int kConsumers = kConsumerWarps * 32;  // 512
-constexpr int kThreads = kConsumers + 32;        // + producer warp
+#ifndef THR_BM25_CW
+#define THR_BM25_CW 16
+#endif
+constexpr int kConsumerWarps = THR_BM25_CW;
+constexpr int kConsumers = kConsumerWarps * 32;                    // 512
+constexpr int kThreads = kConsumers + 32;                          // + producer warp
 constexpr int kMaxBlkDocs = 16384;
-constexpr int kStageCap = 4096;                  // postings per ring stage (32 KB)
-constexpr int kStages = 3;
-constexpr int kCandCap = 4608;                   // >= kStageCap + kMaxSelB (one sparse pass can append a whole stage)
+constexpr int kRingCap = 12288;                  // postings in the ring (96 KB)
+constexpr int kStepCap = 4096;                   // postings per step
+constexpr int kSlots = 8;                        // steps in flight
 constexpr int kMaxSelB = 256;
-constexpr int kScanChunk = 2048;                 // accumulator slots scanned between capacity checks
+constexpr int kCandCap = kStepCap + 2 * kMaxSelB;  // a single-step range can append a whole step after a compaction
+constexpr int kMaxSeg = kMaxTerms;               // one segment per term and step
+constexpr int kPtrDepth = 12;                    // skip entries prefetched ahead
+constexpr int kPtrRing = 16;
 
 struct Posting { uint32_t doc; float imp; };
 
-// A work unit: one query restricted to the doc ranges [r0, r1).  Heavy queries are cut into several
-// units so that no CTA is left streaming one long query while the others idle.
+// A work unit: one query restricted to the doc ranges [r0, r1).
 struct Unit { int q; int r0; int r1; unsigned cost; };
 constexpr int kMaxUnitsPerQuery = 16;
 
-struct StageMeta {
+enum { kLast = 1, kEou = 2, kSingle = 4 };
+
+struct StepMeta {
   int nseg;
-  int last_of_range;     // scan after this step
+  int flags;             // kLast: last step of its range; kSingle: the only step of its range; kEou: end of unit
   int range;             // range index
-  int range_add_bound;   // upper bound of docs this range can append (valid on last step)
-  int end_of_query;      // no data: consumers finish the query
-  int single;            // this step holds ALL postings of the range -> sparse second pass
-  int used;              // postings in this step (sum of seg_count)
-  int seg_term[kMaxTerms + 2];    // query term slot
-  int seg_start[kMaxTerms + 2];   // first valid posting inside the stage buffer
-  int seg_count[kMaxTerms + 2];
-  int pad_;
+  int add_bound;         // upper bound of docs the range can append (valid on the last step)
+  uint2 seg[kMaxSeg];    // .x = first valid posting (ring index) | count << 16,  .y = idf of the term (float bits)
 };
-static_assert(sizeof(StageMeta) % 8 == 0, "mbarriers follow the metadata and need 8-byte alignment");
+static_assert(kRingCap <= 65536 && kStepCap < 65536, "segment start / count are packed into 16 bits each");
+static_assert(sizeof(StepMeta) % 8 == 0, "mbarriers follow the metadata and need 8-byte alignment");
 
 struct Bm25Args {
-  const int64_t* blk_ptr;
+  const int64_t* skip;    // [V * n_blk + 1]
   const Posting* post;
   const float* idf;
   int64_t n_docs;
-  int n_blk, blk_docs, V;
-  int64_t id_base;
+  int n_blk, blk_docs, blk_shift, V;
   const int32_t* q_terms;
   const int32_t* q_off;
   const int32_t* order;   // work units, heaviest first
@@ -81,6 +90,19 @@ struct Bm25Args {
 __device__ __forceinline__ void bar_consumers() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
 }
+// Barrier over the consumer threads that also ORs a predicate: every thread gets the same answer.
+__device__ __forceinline__ bool bar_consumers_or(bool p) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "bar.red.or.pred q, 1, %2, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"((uint32_t)p), "n"(kConsumers)
+      : "memory");
+  return r != 0;
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -88,6 +110,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       :
       : "r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // Block-cooperative (consumer threads only): keep the ksel largest of keys[0..n) in place, n > ksel.
@@ -119,7 +149,7 @@ __device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t
   }
   const uint64_t T = *s_prefix;
   // survivors: read everything first, then rewrite the front
-  constexpr int kPer = kCandCap / kConsumers;
+  constexpr int kPer = (kCandCap + kConsumers - 1) / kConsumers;
   uint64_t mine[kPer];
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
@@ -135,28 +165,38 @@ __device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t
   return T;
 }
 
+constexpr size_t kSmemRing = (size_t)kRingCap * sizeof(Posting);
+constexpr size_t kSmemAcc = (size_t)kMaxBlkDocs * 4;
+constexpr size_t kSmemCand = (size_t)kCandCap * 8;
+constexpr size_t kSmemMeta = (size_t)kSlots * sizeof(StepMeta);
+constexpr size_t kSmemBars = (size_t)2 * kSlots * 8;
+constexpr size_t kSmemPtr = (size_t)kPtrRing * 32 * 8;
+constexpr size_t kSmemMisc = 256 * 4 + kMaxTerms * 8 + 8 + 8 * 4;
+constexpr size_t kBm25Smem = kSmemRing + kSmemAcc + kSmemCand + kSmemMeta + kSmemBars + kSmemPtr + kSmemMisc + 256;
+
 __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  // carve-up
-  Posting* stage_buf = (Posting*)gen;                                         // kStages * kStageCap
-  float* acc = (float*)(gen + (size_t)kStages * kStageCap * sizeof(Posting)); // kMaxBlkDocs
-  uint64_t* cand = (uint64_t*)(acc + kMaxBlkDocs);                            // kCandCap
-  StageMeta* meta = (StageMeta*)(cand + kCandCap);                            // kStages
-  uint64_t* bars = (uint64_t*)(meta + kStages);                               // full[kStages], empty[kStages]
-  uint32_t* hist = (uint32_t*)(bars + 2 * kStages);                           // 256
+  // carve-up (every region keeps 8-byte alignment)
+  Posting* ring = (Posting*)gen;
+  float* acc = (float*)(gen + kSmemRing);
+  uint64_t* cand = (uint64_t*)(acc + kMaxBlkDocs);
+  StepMeta* meta = (StepMeta*)(cand + kCandCap);
+  uint64_t* bars = (uint64_t*)(meta + kSlots);                                // full, empty
+  long long* pring = (long long*)(bars + 2 * kSlots);                         // [kPtrRing][32]
+  uint32_t* hist = (uint32_t*)(pring + kPtrRing * 32);                        // 256
   int* q_term = (int*)(hist + 256);                                           // kMaxTerms
   float* q_idf = (float*)(q_term + kMaxTerms);                                // kMaxTerms
   unsigned long long* s_prefix = (unsigned long long*)(q_idf + kMaxTerms);
-  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=query [4]=nterms
+  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=unit [4]=nterms
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
-  auto empty_bar = [&](int s) { return smem_u32(&bars[kStages + s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[kSlots + s]); };
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), kConsumerWarps);
     }
@@ -165,11 +205,15 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   for (int i = tid; i < kMaxBlkDocs; i += kThreads) acc[i] = 0.f;
   __syncthreads();
 
-  uint32_t it = 0;  // ring step counter, advances identically in producer and consumers
+  uint32_t it = 0;  // step counter, advances identically in all three roles
   const int R = a.blk_docs;
+  // producer-only ring state
+  int head = 0;          // next free posting in the ring
+  uint32_t oldest = 0;   // oldest step whose data may still be in use
+  int my_begin = 0;      // lane j < kSlots: ring offset of the step in slot j
 
   for (;;) {
-    // ---- fetch the next query (whole CTA) ----
+    // ---- fetch the next unit (whole CTA) ----
     __syncthreads();
     if (tid == 0) {
       int w = atomicAdd(a.work_counter, 1);
@@ -200,271 +244,243 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
     if (warp == kConsumerWarps) {
       // ======================= producer warp =======================
       const int my_term = lane < nterms ? q_term[lane] : -1;
-      // pointer pipeline: the (lo, hi) pair of range r + 4 is requested while range r is packed
-      auto load_ptr = [&](int r, int64_t& lo, int64_t& hi) {
-        lo = 0; hi = 0;
-        if (my_term >= 0 && r < r_end) {
-          const int64_t* p = a.blk_ptr + (size_t)r * (a.V + 1) + my_term;
-          lo = __ldg(p);
-          hi = __ldg(p + 1);
+      const float my_idf = lane < nterms ? q_idf[lane] : 0.f;
+      const int64_t* row = a.skip + (size_t)(my_term < 0 ? 0 : my_term) * a.n_blk + r_begin;
+      const int n_ranges = r_end - r_begin;
+      const uint32_t my_pr = smem_u32(pring + lane);
+      auto issue_ptr = [&](int e) {  // skip entry e of this unit: row[e], e in [0, n_ranges]
+        if (my_term >= 0 && e <= n_ranges) cp_async_8(my_pr + (uint32_t)(e % kPtrRing) * 256u, row + e);
+        cp_async_commit();
+      };
+      auto wait_step = [&](uint32_t j) {  // until the consumers released step j
+        mbar_wait_relaxed(empty_bar(j % kSlots), (j / kSlots) & 1u, a.status, 400);
+      };
+      // Room for n postings (even) in the ring for step `it`; returns the ring offset.
+      auto alloc = [&](int n) -> int {
+        while (oldest + kSlots <= it) { wait_step(oldest); ++oldest; }  // the slot itself must be free
+        for (;;) {
+          int pos = -1;
+          if (oldest == it) { head = 0; pos = 0; }  // nothing outstanding
+          else {
+            const int tb = __shfl_sync(0xffffffffu, my_begin, (int)(oldest % kSlots));
+            if (head >= tb) {            // occupied: [tb, head)
+              if (n <= kRingCap - head) pos = head;
+              else if (n < tb) pos = 0;
+            } else if (n < tb - head) {  // occupied: [tb, cap) + [0, head)
+              pos = head;
+            }
+          }
+          if (pos >= 0) {
+            head = pos + n;
+            if (lane == (int)(it % kSlots)) my_begin = pos;
+            return pos;
+          }
+          wait_step(oldest);
+          ++oldest;
         }
       };
-      int64_t l0, h0, l1, h1, l2, h2, l3, h3;
-      load_ptr(r_begin, l0, h0); load_ptr(r_begin + 1, l1, h1); load_ptr(r_begin + 2, l2, h2);
-      load_ptr(r_begin + 3, l3, h3);
-      for (int r = r_begin; r < r_end; ++r) {
-        int64_t lo = l0, hi = h0;
-        l0 = l1; h0 = h1; l1 = l2; h1 = h2; l2 = l3; h2 = h3;
-        load_ptr(r + 4, l3, h3);
+
+      for (int e = 0; e <= kPtrDepth; ++e) issue_ptr(e);
+      for (int i = 0; i < n_ranges; ++i) {
+        issue_ptr(i + kPtrDepth + 1);
+        cp_async_wait<kPtrDepth>();  // entries 0 .. i+1 have landed
+        int64_t lo = 0, hi = 0;
+        if (my_term >= 0) {
+          lo = pring[(i % kPtrRing) * 32 + lane];
+          hi = pring[((i + 1) % kPtrRing) * 32 + lane];
+        }
         int64_t remaining = hi - lo;
-        // upper bound on distinct docs this range can contribute
         long long tot = remaining;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
-        const int add_bound = (int)min((long long)R, tot);
         if (tot == 0) continue;  // nothing in this range for this query
+        const int add_bound = (int)min((long long)R, tot);
         bool first_step = true;
-        {
-          // Fast path (the common case): the whole range fits in one ring stage.  Lanes pack their
-          // segments with one warp scan and every lane issues its own bulk copy — no serial loop.
-          const int cnt_l = (int)remaining;
-          const int slack_l = (int)(lo & 1);
-          const int cp_l = cnt_l > 0 ? ((slack_l + cnt_l + 1) & ~1) : 0;  // postings copied (16 B granules)
-          int incl = cp_l;
+        // Pack the terms' segments into steps of <= kStepCap postings, in term order (normally one step).
+        for (;;) {
+          const bool has = remaining > 0;
+          const int slack = (int)(lo & 1);  // copies start at an even posting (16-byte granules)
+          const long long need_ll = has ? ((slack + remaining + 1) & ~1LL) : 0;
+          const int need = (int)min(need_ll, (long long)(kStepCap + 2));
+          int incl = need;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
           }
-          const int total_cp = __shfl_sync(0xffffffffu, incl, 31);
-          if (total_cp <= kStageCap) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u, a.status, 402);
-            const unsigned have = __ballot_sync(0xffffffffu, cnt_l > 0);
-            const int used_before = incl - cp_l;
-            if (cnt_l > 0) {
-              const int g = __popc(have & ((1u << lane) - 1));
-              meta[s].seg_term[g] = lane;
-              meta[s].seg_start[g] = used_before + slack_l;
-              meta[s].seg_count[g] = cnt_l;
+          const int before = incl - need;
+          int take = 0, cp = 0;
+          if (has) {
+            if (incl <= kStepCap) { take = (int)remaining; cp = need; }
+            else if (before < kStepCap) {  // first term that does not fit: take a piece if it is worth a copy
+              const int room = kStepCap - before - slack - 1;
+              if (room >= 64) { take = (int)min((long long)room, (long long)remaining); cp = (slack + take + 1) & ~1; }
             }
-            __syncwarp();
-            if (lane == 0) {
-              meta[s].nseg = __popc(have);
-              meta[s].last_of_range = 1;
-              meta[s].range = r;
-              meta[s].range_add_bound = add_bound;
-              meta[s].end_of_query = 0;
-              meta[s].single = 1;
-              meta[s].used = (int)tot;
-              mbar_arrive_expect_tx(full_bar(s), (uint32_t)total_cp * 8u);
-            }
-            __syncwarp();
-            if (cnt_l > 0)
-              bulk_g2s(smem_u32(stage_buf + (size_t)s * kStageCap + used_before), a.post + (lo - slack_l),
-                       (uint32_t)cp_l * 8u, full_bar(s));
-            ++it;
-            continue;
           }
-        }
-        // emit steps until every lane's segment is drained (terms in order)
-        while (true) {
-          unsigned live = __ballot_sync(0xffffffffu, remaining > 0);
-          if (!live) break;
-          const int cur = __ffs(live) - 1;
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u, a.status, 400);
-          // greedy packing in term order; each segment is copied from its 16-byte-aligned start
-          int used = 0;  // postings used in the stage (including alignment slack)
-          int nseg = 0, npost = 0;
-          uint32_t bytes_total = 0;
-          for (int t = cur; t < nterms; ++t) {
-            int64_t rem_t = __shfl_sync(0xffffffffu, remaining, t);
-            int64_t lo_t = __shfl_sync(0xffffffffu, lo, t);
-            if (rem_t <= 0) continue;
-            const int slack = (int)(lo_t & 1);           // start is 8-byte aligned; copy from the even posting
-            int room = kStageCap - used - slack - 1;     // -1: the copy length is rounded up to 2 postings
-            if (room < 64 && nseg > 0) break;            // keep pieces reasonably long
-            if (room <= 0) break;
-            int take = (int)min((int64_t)room, rem_t);
-            const int64_t src_first = lo_t - slack;
-            const int cp_postings = (slack + take + 1) & ~1;
-            if (lane == 0) {
-              meta[s].seg_term[nseg] = t;
-              meta[s].seg_start[nseg] = used + slack;
-              meta[s].seg_count[nseg] = take;
-            }
-            if (lane == t) {
-              bulk_g2s(smem_u32(stage_buf + (size_t)s * kStageCap + used), a.post + src_first,
-                       (uint32_t)cp_postings * 8u, full_bar(s));
-              lo += take;
-              remaining -= take;
-            }
-            bytes_total += (uint32_t)cp_postings * 8u;
-            used += cp_postings;
-            npost += take;
-            ++nseg;
-            if (take < rem_t) break;  // stage full in the middle of this term
+          int cincl = cp;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, cincl, d);
+            if (lane >= d) cincl += v;
           }
-          unsigned still = __ballot_sync(0xffffffffu, remaining > 0);
+          const int total_cp = __shfl_sync(0xffffffffu, cincl, 31);
+          const int off = cincl - cp;
+          const unsigned have = __ballot_sync(0xffffffffu, take > 0);
+          const unsigned still = __ballot_sync(0xffffffffu, remaining - take > 0);
+          const int s = it % kSlots;
+          const int pos = alloc(total_cp);
+          if (take > 0) {
+            const int g = __popc(have & ((1u << lane) - 1));
+            meta[s].seg[g] = make_uint2((uint32_t)(pos + off + slack) | ((uint32_t)take << 16), __float_as_uint(my_idf));
+          }
+          __syncwarp();
           if (lane == 0) {
-            meta[s].nseg = nseg;
-            meta[s].last_of_range = still ? 0 : 1;
-            meta[s].range = r;
-            meta[s].range_add_bound = add_bound;
-            meta[s].end_of_query = 0;
-            meta[s].single = (first_step && !still) ? 1 : 0;
-            meta[s].used = npost;
+            meta[s].nseg = __popc(have);
+            meta[s].flags = (still ? 0 : kLast) | ((first_step && !still) ? kSingle : 0);
+            meta[s].range = r_begin + i;
+            meta[s].add_bound = add_bound;
             // metadata is written with generic stores; the arrive has release semantics
-            mbar_arrive_expect_tx(full_bar(s), bytes_total);
+            mbar_arrive_expect_tx(full_bar(s), (uint32_t)total_cp * 8u);
           }
+          __syncwarp();
+          if (take > 0)
+            bulk_g2s(smem_u32(ring + pos + off), a.post + (lo - slack), (uint32_t)cp * 8u, full_bar(s));
+          lo += take;
+          remaining -= take;
           first_step = false;
           ++it;
-          __syncwarp();
+          if (!still) break;
         }
       }
-      // end-of-query marker
+      // end-of-unit marker
       {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u, a.status, 401);
+        const int s = it % kSlots;
+        (void)alloc(0);
         if (lane == 0) {
           meta[s].nseg = 0;
-          meta[s].last_of_range = 0;
-          meta[s].end_of_query = 1;
-          meta[s].single = 0;
-          meta[s].used = 0;
+          meta[s].flags = kEou;
           mbar_arrive(full_bar(s));
         }
         ++it;
         __syncwarp();
       }
+      cp_async_wait<0>();
     } else {
       // ======================= consumers =======================
+      // The hot loops address shared memory with 32-bit shared-space addresses (ld/st.shared).
       float tau = 0.f;  // only score > 0 is eligible; raised by compactions
+      volatile int* v_cnt = &s_int[2];
+      const uint32_t ring_addr = smem_u32(ring), acc_addr = smem_u32(acc);
+      // rare path: one candidate per calling lane
+      auto emit1 = [&](float v, uint32_t doc) {
+        const int pos = atomicAdd(&s_int[2], 1);
+        if (pos < kCandCap) cand[pos] = pack_key(v, doc);
+        else dev_report(a.status, THR_EOVERFLOW, 430, pos);  // excluded by the capacity votes; keep it loud
+      };
+      auto compact = [&]() {
+        const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
+        tau = key_score(T);
+        if (tid == 0) s_int[2] = s_int[1];
+        bar_consumers();
+      };
       for (;;) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
+        const int s = it % kSlots;
+        const uint32_t ph = (it / kSlots) & 1u;
         mbar_wait(full_bar(s), ph, a.status, 410);
         ++it;
-        const StageMeta& m = meta[s];
-        const int nseg = m.nseg;
-        const bool eoq = m.end_of_query != 0;
-        const bool last = m.last_of_range != 0;
-        const bool single = m.single != 0;
-        const int used = m.used;
-        const int r = m.range;
-        const int add_bound = m.range_add_bound;
-        Posting* sb = stage_buf + (size_t)s * kStageCap;
-        const uint32_t doc0 = (uint32_t)r * (uint32_t)R;
-        // ---- pass 1: accumulate, term by term ----
-        int prev_term = -1;
-        for (int g = 0; g < nseg; ++g) {
-          const int t = m.seg_term[g];
-          const int st = m.seg_start[g];
-          const int cn = m.seg_count[g];
-          if (prev_term >= 0 && t != prev_term) bar_consumers();  // term boundary: same doc may recur
-          prev_term = t;
-          const float w = q_idf[t];
-          for (int i = tid; i < cn; i += kConsumers) {
-            const Posting p = sb[st + i];
-            const uint32_t slot = p.doc - doc0;
-            const float old = acc[slot];
-            acc[slot] = __fadd_rn(old, __fmul_rn(w, p.imp));
-            if (single && old == 0.f) sb[st + i].doc = p.doc | 0x80000000u;  // first touch owns the doc
+        const uint32_t meta_addr = smem_u32(&meta[s]);
+        int nseg, flags, range, add_bound;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(nseg), "=r"(flags), "=r"(range), "=r"(add_bound) : "r"(meta_addr));
+        if (flags & kEou) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(s));
+          break;
+        }
+        const uint32_t doc0 = (uint32_t)range << a.blk_shift;
+        const uint32_t acc0 = acc_addr - doc0 * 4u;  // &acc[doc - doc0] == acc0 + doc * 4 (mod 2^32)
+        const bool single = (flags & kSingle) != 0;
+        const bool last = (flags & kLast) != 0;
+        // tight: even a list compacted to k could overflow (only ranges spread over several steps) — those
+        // vote per scan chunk instead.  Otherwise a true vote implies count > k, which the compaction needs.
+        const bool tight = a.k + add_bound > kCandCap;
+        bool vote = false;
+        // ---- pass 1: accumulate, one term at a time ----
+        uint32_t seg_addr = meta_addr + 16u;
+        for (int g = 0; g < nseg; ++g, seg_addr += 8u) {
+          uint32_t pw;
+          float w;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(pw), "=f"(w) : "r"(seg_addr));
+          const uint32_t end = ring_addr + ((pw & 0xffffu) + (pw >> 16)) * 8u;
+          for (uint32_t pa = ring_addr + ((pw & 0xffffu) + (uint32_t)tid) * 8u; pa < end; pa += kConsumers * 8u) {
+            uint32_t doc;
+            float imp, old;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(doc), "=f"(imp) : "r"(pa));
+            const uint32_t aa = acc0 + doc * 4u;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old) : "r"(aa));
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(__fadd_rn(old, __fmul_rn(w, imp))) : "memory");
+            // the first posting to touch a doc owns it in pass 2
+            if (single && old == 0.f) asm volatile("st.shared.b32 [%0], %1;" ::"r"(pa), "r"(doc | 0x80000000u) : "memory");
           }
+          // term boundary: the next term (or the next step) may hit the same docs
+          if (g + 1 == nseg && last && !tight) vote = bar_consumers_or(*v_cnt + add_bound > kCandCap);
+          else bar_consumers();
         }
         if (!single) {
-          // this stage's shared buffer is free once every consumer warp has read it
           __syncwarp();
-          if (lane == 0) mbar_arrive(empty_bar(s));
-        }
-        if (eoq) break;
-        if (nseg > 0) bar_consumers();  // all accumulates of this step done
-
-        if (single) {
-          // ---- pass 2 (sparse): owners read the final score, append if > tau, re-zero ----
-          int cnt_now = s_int[2];
-          if (cnt_now + used > kCandCap) {  // block-uniform; implies cnt_now > kMaxSelB >= k
-            const uint64_t T = block_compact_topk(cand, cnt_now, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-            tau = key_score(T);
-            if (tid == 0) s_int[2] = s_int[1];
-            bar_consumers();
-          }
-          for (int g = 0; g < nseg; ++g) {
-            const int st = m.seg_start[g];
-            const int cn = m.seg_count[g];
-            for (int i0 = warp * 32; i0 < cn; i0 += kConsumers) {
-              const int i = i0 + lane;
-              bool emit = false;
-              uint64_t key = 0;
-              if (i < cn) {
-                const uint32_t d = sb[st + i].doc;
-                if (d & 0x80000000u) {
-                  const uint32_t doc = d & 0x7fffffffu;
-                  const uint32_t slot = doc - doc0;
-                  const float v = acc[slot];
-                  acc[slot] = 0.f;
-                  emit = v > tau;
-                  key = pack_key(v, doc);
-                }
-              }
-              const unsigned bal = __ballot_sync(0xffffffffu, emit);
-              if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_int[2], __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (emit) cand[base + __popc(bal & ((1u << lane) - 1))] = key;
-              }
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_bar(s));
-          bar_consumers();  // slots re-zeroed and appends visible before the next range
-          continue;
+          if (lane == 0) mbar_arrive(empty_bar(s));  // this warp no longer reads the step's postings
         }
         if (!last) continue;
 
-        // ---- fallback for ranges spread over several steps: scan all accumulators ----
-        const int ndocs_r = (int)min((int64_t)R, a.n_docs - (int64_t)r * R);
-        int cnt_now = s_int[2];
-        const bool tight = cnt_now + add_bound > kCandCap;  // block-uniform
-        for (int c0 = 0; c0 < ndocs_r; c0 += kScanChunk) {
-          if (tight) {
-            bar_consumers();
-            cnt_now = s_int[2];
-            if (cnt_now + kScanChunk > kCandCap) {
-              const uint64_t T = block_compact_topk(cand, cnt_now, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-              tau = key_score(T);
-              if (tid == 0) s_int[2] = s_int[1];
-              bar_consumers();
-            }
-          }
-          const int c1 = min(c0 + kScanChunk, ndocs_r);
-          for (int i = c0 + tid * 4; i < c1; i += kConsumers * 4) {
-            float4 v = *reinterpret_cast<float4*>(&acc[i]);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            bool any = false;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (vv[e] != 0.f) any = true;
-              if (vv[e] > tau && i + e < c1) {
-                int pos = atomicAdd(&s_int[2], 1);
-                if (pos < kCandCap) cand[pos] = pack_key(vv[e], doc0 + (uint32_t)(i + e));
-                else dev_report(a.status, THR_EOVERFLOW, 420, pos);
+        // ---- range complete: collect its docs ----
+        if (vote) compact();
+        if (single) {
+          // sparse: owners read the final score, append if > tau, re-zero the slot
+          seg_addr = meta_addr + 16u;
+          for (int g = 0; g < nseg; ++g, seg_addr += 8u) {
+            uint32_t pw;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pw) : "r"(seg_addr));
+            const uint32_t end = ring_addr + ((pw & 0xffffu) + (pw >> 16)) * 8u;
+            for (uint32_t pa = ring_addr + ((pw & 0xffffu) + (uint32_t)tid) * 8u; pa < end; pa += kConsumers * 8u) {
+              uint32_t d;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(d) : "r"(pa));
+              if (d & 0x80000000u) {
+                const uint32_t doc = d & 0x7fffffffu;
+                const uint32_t aa = acc0 + doc * 4u;
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(aa));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(0.f) : "memory");
+                if (v > tau) emit1(v, doc);
               }
             }
-            if (any) *reinterpret_cast<float4*>(&acc[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(s));
+        } else {
+          // the range came in several steps: scan the accumulators
+          for (int c0 = 0; c0 < R; c0 += kConsumers * 4) {  // uniform trip count: the vote is a block barrier
+            if (tight && bar_consumers_or(*v_cnt + kConsumers * 4 > kCandCap)) compact();
+            const int c = c0 + tid * 4;
+            if (c < R) {
+              float4* p4 = reinterpret_cast<float4*>(&acc[c]);
+              const float4 v = *p4;
+              if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                *p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t d = doc0 + (uint32_t)c;
+                if (v.x > tau) emit1(v.x, d);
+                if (v.y > tau) emit1(v.y, d + 1);
+                if (v.z > tau) emit1(v.z, d + 2);
+                if (v.w > tau) emit1(v.w, d + 3);
+              }
+            }
           }
         }
-        bar_consumers();  // scan complete before the next range accumulates
+        bar_consumers();  // slots re-zeroed and appends visible before the next range accumulates
       }
 
-      // ---- end of query: final top-k, sorted ----
+      // ---- end of unit: final top-k, sorted ----
       bar_consumers();
-      int n = s_int[2];
+      int n = *v_cnt;
       if (n > a.k) {
         (void)block_compact_topk(cand, n, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
         n = s_int[1];
@@ -492,18 +508,13 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   }
 }
 
-// cost[q] = total postings of the query's terms.
-__global__ void bm25_df_kernel(const int64_t* blk_ptr, int n_blk, int V, int64_t* df) {
+__global__ void bm25_df_kernel(const int64_t* skip, int n_blk, int V, int64_t* df) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V) return;
-  int64_t s = 0;
-  for (int r = 0; r < n_blk; ++r) {
-    const int64_t* p = blk_ptr + (size_t)r * (V + 1) + t;
-    s += p[1] - p[0];
-  }
-  df[t] = s;
+  df[t] = skip[(size_t)(t + 1) * n_blk] - skip[(size_t)t * n_blk];
 }
 
+// cost[q] = total postings of the query's terms.
 __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, const int64_t* df, int V,
                                  int B, unsigned long long* keys) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -517,7 +528,9 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
   keys[q] = ((unsigned long long)c << 32) | (unsigned)(0xffffffffu - (unsigned)q);
 }
 
-// Single block: cut queries into units of roughly equal posting count.
+// Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
+// per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
+constexpr unsigned long long kRangeCost = 512;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_sms, Unit* units, int* unit_base,
                                                           int* total_units, int* work_counter) {
@@ -528,17 +541,17 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long lon
   if (tid == 0) { s_tot = 0; s_carry = 0; *work_counter = 0; }
   __syncthreads();
   unsigned long long part = 0;
-  for (int q = tid; q < B; q += 1024) part += keys[q] >> 32;
+  for (int q = tid; q < B; q += 1024) part += (keys[q] >> 32) + kRangeCost * (unsigned long long)n_blk;
   atomicAdd(&s_tot, part);
   __syncthreads();
-  unsigned long long target = s_tot / (unsigned long long)(num_sms * 2) + 1;
-  if (target < 32768ull) target = 32768ull;
+  unsigned long long target = s_tot / (unsigned long long)(num_sms * 3) + 1;
+  if (target < 65536ull) target = 65536ull;
   for (int q0 = 0; q0 < B; q0 += 1024) {
     const int q = q0 + tid;
     int nu = 0;
     unsigned long long c = 0;
     if (q < B) {
-      c = keys[q] >> 32;
+      c = (keys[q] >> 32) + kRangeCost * (unsigned long long)n_blk;
       nu = (int)((c + target - 1) / target);
       if (nu < 1) nu = 1;
       if (nu > kMaxUnitsPerQuery) nu = kMaxUnitsPerQuery;
@@ -633,18 +646,14 @@ __global__ void __launch_bounds__(256) bm25_merge_kernel(const uint64_t* part_ke
   }
 }
 
-constexpr size_t kBm25Smem = (size_t)kStages * kStageCap * 8 + (size_t)kMaxBlkDocs * 4 +
-                             (size_t)kCandCap * 8 + kStages * sizeof(StageMeta) + 2 * kStages * 8 +
-                             256 * 4 + kMaxTerms * 8 + 8 + 8 * 4 + 256;
-
 }  // namespace
 
 struct thr_bm25_state {
-  const int64_t* blk_ptr;
+  const int64_t* skip;
   const void* post;
   const float* idf;
   int64_t n_docs;
-  int n_blk, blk_docs, V;
+  int n_blk, blk_docs, blk_shift, V;
   int64_t id_base;
   int64_t* df;  // [V] device
 };
@@ -659,27 +668,30 @@ void thr_bm25_state_free(thr_handle* h) {
 
 extern "C" {
 
-int thr_bm25_index_set(thr_handle* h, const int64_t* blk_ptr, const void* postings, const float* idf,
+int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings, const float* idf,
                        int64_t n_docs, int32_t n_blk, int32_t blk_docs, int32_t V, int64_t id_base) {
   if (!h) return THR_EINVAL;
   cudaSetDevice(h->device);
-  THR_REQUIRE(h, blk_ptr && postings && idf, "thr_bm25_index_set: NULL argument");
+  THR_REQUIRE(h, skip && postings && idf, "thr_bm25_index_set: NULL argument");
   THR_REQUIRE(h, n_docs >= 1 && V >= 1 && n_blk >= 1, "thr_bm25_index_set: empty index");
-  if (blk_docs % 1024 != 0 || blk_docs < 1024 || blk_docs > kMaxBlkDocs)
-    return thr_fail(h, THR_EUNSUPPORTED, "thr_bm25_index_set: blk_docs = %d must be a multiple of 1024 in [1024, %d]",
+  int shift = 0;
+  while ((1 << shift) < blk_docs) ++shift;
+  if ((1 << shift) != blk_docs || blk_docs < 1024 || blk_docs > kMaxBlkDocs)
+    return thr_fail(h, THR_EUNSUPPORTED, "thr_bm25_index_set: blk_docs = %d must be a power of two in [1024, %d]",
                     blk_docs, kMaxBlkDocs);
   THR_REQUIRE(h, (int64_t)n_blk * blk_docs >= n_docs && (int64_t)(n_blk - 1) * blk_docs < n_docs,
               "thr_bm25_index_set: n_blk does not match n_docs / blk_docs");
   THR_REQUIRE(h, n_docs < ((int64_t)1 << 31), "thr_bm25_index_set: more than 2^31 docs per shard (bit 31 of a staged doc id is the owner flag)");
   THR_REQUIRE(h, ((uintptr_t)postings & 15u) == 0, "thr_bm25_index_set: postings must be 16-byte aligned");
+  THR_REQUIRE(h, ((uintptr_t)skip & 7u) == 0, "thr_bm25_index_set: skip must be 8-byte aligned");
   thr_bm25_state_free(h);
   thr_bm25_state* st = (thr_bm25_state*)calloc(1, sizeof(thr_bm25_state));
   if (!st) return thr_fail(h, THR_ENOMEM, "out of host memory");
-  st->blk_ptr = blk_ptr; st->post = postings; st->idf = idf; st->n_docs = n_docs; st->n_blk = n_blk;
-  st->blk_docs = blk_docs; st->V = V; st->id_base = id_base;
+  st->skip = skip; st->post = postings; st->idf = idf; st->n_docs = n_docs; st->n_blk = n_blk;
+  st->blk_docs = blk_docs; st->blk_shift = shift; st->V = V; st->id_base = id_base;
   cudaError_t e = cudaMalloc((void**)&st->df, (size_t)V * sizeof(int64_t));
   if (e != cudaSuccess) { free(st); return thr_fail(h, THR_ENOMEM, "cudaMalloc(df): %s", cudaGetErrorString(e)); }
-  bm25_df_kernel<<<(V + 255) / 256, 256>>>(blk_ptr, n_blk, V, st->df);
+  bm25_df_kernel<<<(V + 255) / 256, 256>>>(skip, n_blk, V, st->df);
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -733,8 +745,8 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   THR_CHECK_LAUNCH(h, "bm25_order_kernel");
 
   Bm25Args a;
-  a.blk_ptr = st->blk_ptr; a.post = (const Posting*)st->post; a.idf = st->idf; a.n_docs = st->n_docs;
-  a.n_blk = st->n_blk; a.blk_docs = st->blk_docs; a.V = st->V; a.id_base = st->id_base;
+  a.skip = st->skip; a.post = (const Posting*)st->post; a.idf = st->idf; a.n_docs = st->n_docs;
+  a.n_blk = st->n_blk; a.blk_docs = st->blk_docs; a.blk_shift = st->blk_shift; a.V = st->V;
   a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.units = units; a.total_units = total_units;
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.status = h->d_status;

@@ -184,6 +184,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Same with a suspend-time hint (ns): the warp may sleep in hardware until the phase completes or the
+// hint elapses, instead of burning issue slots in a spin loop.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Acquire at cluster scope: needed when the arrive came from the peer CTA.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -229,6 +242,23 @@ __device__ __forceinline__ bool mbar_wait_impl(uint32_t bar, uint32_t parity, th
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, thr_dev_status* st,
                                           int where) {
   return mbar_wait_impl<false>(bar, parity, st, where);
+}
+// For latency-tolerant roles (producers waiting for a free slot, helpers waiting for data): sleeps in
+// hardware between polls so that the waiting warp leaves the issue slots to the working warps.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, thr_dev_status* st,
+                                                  int where) {
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return true;
+    if ((spin & 63u) == 0) {
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > THR_WATCHDOG_NS) {
+        dev_report(st, THR_ETIMEOUT, where, (long long)parity);
+        __trap();
+      }
+    }
+  }
 }
 __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity,
                                                   thr_dev_status* st, int where) {

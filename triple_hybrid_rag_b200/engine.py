@@ -110,16 +110,16 @@ class Engine:
         return ids, sc, cnt, gap
 
     # -- K2 BM25 ----------------------------------------------------------------------------
-    def bm25_index_set(self, blk_ptr: torch.Tensor, postings: torch.Tensor, idf: torch.Tensor, n_docs: int,
+    def bm25_index_set(self, skip: torch.Tensor, postings: torch.Tensor, idf: torch.Tensor, n_docs: int,
                        blk_docs: int, V: int, id_base: int = 0):
-        blk_ptr = self._dev(blk_ptr, torch.int64, "blk_ptr")
+        skip = self._dev(skip, torch.int64, "skip")
         postings = self._dev(postings, torch.int32, "postings")  # [nnz + pad, 2] raw {doc, impact bits}
         idf = self._dev(idf, torch.float32, "idf")
         n_blk = (n_docs + blk_docs - 1) // blk_docs
-        if blk_ptr.numel() != n_blk * (V + 1):
-            raise ValueError("blk_ptr must have n_blk * (V + 1) entries")
-        self._keep.update(blk_ptr=blk_ptr, postings=postings, idf=idf)
-        self._check(self._lib.thr_bm25_index_set(self._h, _ptr(blk_ptr), _ptr(postings), _ptr(idf), n_docs, n_blk,
+        if skip.numel() != V * n_blk + 1:
+            raise ValueError("skip must have V * n_blk + 1 entries")
+        self._keep.update(skip=skip, postings=postings, idf=idf)
+        self._check(self._lib.thr_bm25_index_set(self._h, _ptr(skip), _ptr(postings), _ptr(idf), n_docs, n_blk,
                                                  blk_docs, V, id_base))
 
     def bm25_topk(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int

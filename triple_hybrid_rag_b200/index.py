@@ -1,11 +1,12 @@
 """Resident indexes for the hot path.
 
-BM25Index builds the blocked inverted index libthr's K2 kernel reads (layout in include/thr.h):
-documents are cut into ranges of `blk_docs`, postings are ordered (range, term, doc) and stored as
-{uint32 doc, float32 impact}.  Building is torch plumbing (sort / bincount / cumsum) and runs on
-whatever device the inputs live on; it is the step before the hot path.
-The BM25 formula is the one oracle/bm25.py states; idf is always computed with numpy on the host
-so that both sides use the same libm.
+BM25Index builds the inverted index libthr's K2 kernel reads (layout in include/thr.h): postings in
+term-major CSR order (doc ascending inside a term) stored as {uint32 doc, float32 impact}, plus a
+skip table skip[t * n_blk + r] = first posting of term t whose doc lies in doc range r (ranges of
+`blk_docs` docs).  Building is torch plumbing (sort / bincount / cumsum) and runs on whatever device
+the inputs live on; it is the step before the hot path.  The BM25 formula is
+the one oracle/bm25.py states; idf is always computed with numpy on the host so that both sides
+use the same libm.
 """
 from __future__ import annotations
 
@@ -30,7 +31,7 @@ def bm25_impacts(tf: torch.Tensor, dl: torch.Tensor, avgdl: float, k1: float, b:
 
 @dataclass
 class BM25Index:
-    blk_ptr: torch.Tensor    # int64 [n_blk * (V + 1)]
+    skip: torch.Tensor       # int64 [V * n_blk + 1]
     postings: torch.Tensor   # int32 [nnz + 2, 2]: {doc (u32 bits), impact (f32 bits)}, 16 B tail padding
     idf: torch.Tensor        # float32 [V]
     df: torch.Tensor         # int64 [V] (this shard)
@@ -60,62 +61,74 @@ class BM25Index:
         if avgdl is None:
             avgdl = float(doc_len.to(torch.float64).mean().item())
         imp = bm25_impacts(tf, doc_len.to(dev)[doc], avgdl, k1, b)
-        blk_key = (doc // R) * V + term
-        order = torch.argsort(blk_key * R + (doc % R))
-        counts = torch.bincount(blk_key, minlength=n_blk * V)
-        excl = torch.zeros(n_blk * V + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(counts, 0, out=excl[1:])
-        ptr = torch.empty((n_blk, V + 1), dtype=torch.int64, device=dev)
-        ptr[:, :V] = excl[:-1].view(n_blk, V)
-        ptr[:, V] = excl[V::V]
+        order = torch.argsort(term * n_docs + doc)          # (term, doc)
+        counts = torch.bincount(term * n_blk + doc // R, minlength=V * n_blk)
+        skip = torch.zeros(V * n_blk + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=skip[1:])
         nnz = int(doc.numel())
         post = torch.zeros((nnz + 2, 2), dtype=torch.int32, device=dev)
-        post[:nnz, 0] = doc[order].to(torch.int32)  # n_docs < 2^31 per shard here; kernel reads u32
+        post[:nnz, 0] = doc[order].to(torch.int32)  # u32 bit pattern; shards hold < 2^31 docs here
         post[:nnz, 1] = imp[order].view(torch.int32)
         df = torch.bincount(term, minlength=V)
         if idf is None:
             idf = bm25_idf(df, n_docs_global or n_docs)
-        return BM25Index(ptr.reshape(-1), post, idf.to(torch.float32).to(dev), df, n_docs, R, V, nnz, k1, b, avgdl)
+        return BM25Index(skip, post, idf.to(torch.float32).to(dev), df, n_docs, R, V, nnz, k1, b, avgdl)
 
     @staticmethod
     def concat(parts: Sequence["BM25Index"], idf: Optional[torch.Tensor] = None,
                n_docs_global: Optional[int] = None) -> "BM25Index":
-        """Concatenate indexes of consecutive doc ranges (every part but the last must hold a whole
-        number of blocks; doc ids inside each part are local to the part and get rebased here)."""
+        """Merge indexes of consecutive doc ranges (every part but the last must hold a whole number
+        of ranges; doc ids inside each part are local to the part and get rebased here).  Term-major
+        order means a term's postings are the concatenation, in part order, of its per-part lists."""
         p0 = parts[0]
         dev = p0.postings.device
-        ptrs, posts = [], []
-        base_post, base_doc = 0, 0
-        df = torch.zeros_like(p0.df)
+        V = p0.V
         for i, p in enumerate(parts):
-            assert p.blk_docs == p0.blk_docs and p.V == p0.V
+            assert p.blk_docs == p0.blk_docs and p.V == V
             if i + 1 < len(parts):
-                assert p.n_docs % p.blk_docs == 0, "only the last part may end with a partial block"
-            ptrs.append(p.blk_ptr + base_post)
-            pp = p.postings[:p.nnz].clone()
-            pp[:, 0] += base_doc
-            posts.append(pp)
-            base_post += p.nnz
+                assert p.n_docs % p.blk_docs == 0, "only the last part may end with a partial range"
+        counts = torch.cat([(p.skip[1:] - p.skip[:-1]).view(V, p.n_blk) for p in parts], dim=1)
+        n_blk = counts.shape[1]
+        skip = torch.zeros(V * n_blk + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts.reshape(-1), 0, out=skip[1:])
+        del counts
+        nnz = int(skip[-1].item())
+        post = torch.zeros((nnz + 2, 2), dtype=torch.int32, device=dev)
+        cursor = skip[:-1].view(V, n_blk)[:, 0].clone()     # where each term's next part goes
+        df = torch.zeros(V, dtype=torch.int64, device=dev)
+        ar_v = torch.arange(V, device=dev)
+        base_doc = 0
+        for p in parts:
+            df_p = p.df.to(dev)
+            term_of = torch.repeat_interleave(ar_v, df_p)
+            local_start = p.skip[:-1].view(V, p.n_blk)[:, 0]
+            dest = cursor[term_of] + (torch.arange(p.nnz, device=dev) - local_start[term_of])
+            del term_of
+            src = p.postings[:p.nnz]
+            post[dest, 0] = src[:, 0] + base_doc
+            post[dest, 1] = src[:, 1]
+            del dest
+            cursor += df_p
+            df += df_p
             base_doc += p.n_docs
-            df += p.df
-        posts.append(torch.zeros((2, 2), dtype=torch.int32, device=dev))
         if idf is None:
             idf = bm25_idf(df, n_docs_global or base_doc)
-        return BM25Index(torch.cat(ptrs), torch.cat(posts), idf.to(torch.float32).to(dev), df, base_doc,
-                         p0.blk_docs, p0.V, base_post, p0.k1, p0.b, p0.avgdl)
+        return BM25Index(skip, post, idf.to(torch.float32).to(dev), df, base_doc, p0.blk_docs, V, nnz,
+                         p0.k1, p0.b, p0.avgdl)
 
     def to(self, device) -> "BM25Index":
-        return BM25Index(self.blk_ptr.to(device), self.postings.to(device), self.idf.to(device), self.df.to(device),
+        return BM25Index(self.skip.to(device), self.postings.to(device), self.idf.to(device), self.df.to(device),
                          self.n_docs, self.blk_docs, self.V, self.nnz, self.k1, self.b, self.avgdl)
 
     def algorithmic_bytes(self, queries: Sequence[Sequence[int]]) -> int:
-        """sum over queries and terms of df_t * 8 B (+ 16 B of pointers per term and block)."""
+        """sum over queries and terms of df_t * 8 B of postings + 8 B of skip entry per
+        (term, range)."""
         df = self.df.cpu()
         tot = 0
         for q in queries:
             for t in q:
                 if 0 <= t < self.V:
-                    tot += int(df[t]) * 8 + 16 * self.n_blk
+                    tot += int(df[t]) * 8 + 8 * self.n_blk
         return tot
 
 

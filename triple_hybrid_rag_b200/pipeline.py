@@ -64,7 +64,7 @@ class TripleHybridSearcher:
     def set_bm25(self, index: BM25Index, id_base: int = 0):
         d = index.to(self.engine.device)
         self.bm25 = d
-        self.engine.bm25_index_set(d.blk_ptr, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
+        self.engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
         self.has_bm25 = True
 
     # ---- one batch, device tensors in / out ------------------------------------------------
