@@ -105,14 +105,6 @@ def make_config(args, world: int):
             "rerank": "MaxSim (K4) is not part of this step; see tests and DESIGN.md"}
 
 
-def shard_bounds(n: int, world: int):
-    b = [0]
-    for r in range(1, world):
-        b.append(min(n, (n * r // world) // ALIGN * ALIGN))
-    b.append(n)
-    return b
-
-
 def cpu_baseline(args, threads=None):
     """CPU port on a bounded sample of the same workload; returns the cpu_baseline dict + QPS."""
     import numpy as np
@@ -179,7 +171,7 @@ def main():
     from triple_hybrid_rag_b200 import synth
     from triple_hybrid_rag_b200.engine import Engine
     from triple_hybrid_rag_b200.index import BM25Index, bm25_idf, pack_queries
-    from triple_hybrid_rag_b200.pipeline import TripleHybridSearcher
+    from triple_hybrid_rag_b200.pipeline import TripleHybridSearcher, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +188,7 @@ def main():
 
     eng = Engine(dev)
     searcher = TripleHybridSearcher(eng, group)
-    bounds = shard_bounds(N, world)
+    bounds = shard_bounds(N, world, ALIGN)
     lo, hi = bounds[rank], bounds[rank + 1]
 
     # ---- resident corpus (generated on the device, block-wise) ----

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 2
+#define THR_ABI_VERSION 3
 
 enum {
   THR_OK = 0,
@@ -174,6 +174,18 @@ int thr_fuse(thr_handle* h, int variant, int tie_mode, int B,
              int top_k, int max_out,
              int64_t* out_ids, double* out_rrf, int32_t* out_ranks, double* out_raw,
              int32_t* out_count, void* stream);
+
+/* RAG2Retriever._fuse_rrf   src/voice_agent/rag2/retrieval.py:358-376
+ * The reference's own signature: candidates that already carry their 1-based channel ranks.
+ * Per query q with candidates [off[q], off[q+1]) (at most 1024): ranks [n,3] int32 in the order
+ * lexical, semantic, graph; 0 = absent (Python truthiness of `c.lexical_rank`).  weights [B,3].
+ *   out_rrf   [n] double : rrf_score of candidate i, bit-identical to the Python floats
+ *   out_order [n] int32  : for each query, candidate indices (relative to off[q]) in the order of
+ *                          sorted(candidates, key=rrf_score, reverse=True) — stable, ties keep input order.
+ */
+int thr_fuse_ranked(thr_handle* h, int B, const int32_t* off, const int32_t* ranks,
+                    const double* weights, int rrf_k, double* out_rrf, int32_t* out_order,
+                    void* stream);
 
 /* RAG2Retriever._apply_safety   src/voice_agent/rag2/retrieval.py:461-495
  * Per query q with candidates [off[q], off[q+1]) in their current (post-rerank) order:

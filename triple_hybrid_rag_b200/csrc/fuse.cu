@@ -273,6 +273,62 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
   }
 }
 
+// RAG2Retriever._fuse_rrf on candidates that already carry their channel ranks
+// (src/voice_agent/rag2/retrieval.py:358-376): score = 0.0 (+ w_lex/(k+r_lex)) (+ w_sem/(k+r_sem))
+// (+ w_graph/(k+r_graph)), a channel contributing when its rank is truthy (non-zero); then Python's
+// stable sorted(..., reverse=True): descending score, equal scores keep their input order.
+__global__ void __launch_bounds__(kFuseThreads) fuse_ranked_kernel(const int32_t* off, const int32_t* ranks,
+                                                                   const double* weights, int rrf_k,
+                                                                   double* out_rrf, int32_t* out_order,
+                                                                   thr_dev_status* status) {
+  __shared__ double s_rrf[kSortPad];
+  __shared__ uint16_t perm[kSortPad];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int lo = off[q];
+  int n = off[q + 1] - lo;
+  if (n > kSortPad) {
+    if (tid == 0) dev_report(status, THR_EOVERFLOW, 320, n);
+    n = kSortPad;
+  }
+  const double w[3] = {weights[q * 3 + 0], weights[q * 3 + 1], weights[q * 3 + 2]};
+  for (int i = tid; i < kSortPad; i += kFuseThreads) {
+    double rrf = 0.0;
+    if (i < n) {
+      for (int c = 0; c < 3; ++c) {
+        const int r = ranks[(size_t)(lo + i) * 3 + c];
+        if (r != 0) rrf = __dadd_rn(rrf, __ddiv_rn(w[c], (double)(rrf_k + r)));
+      }
+      out_rrf[lo + i] = rrf;
+    }
+    s_rrf[i] = rrf;
+    perm[i] = i < n ? (uint16_t)i : 0xffff;
+  }
+  __syncthreads();
+  int P = 32;
+  while (P < n) P <<= 1;
+  auto before = [&](uint16_t x, uint16_t y) -> bool {
+    if (x == 0xffff) return false;
+    if (y == 0xffff) return true;
+    const double rx = s_rrf[x], ry = s_rrf[y];
+    if (rx != ry) return rx > ry;
+    return x < y;
+  };
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P >> 1); i += kFuseThreads) {
+        int a = ((i / stride) * (stride << 1)) + (i % stride);
+        int b = a + stride;
+        bool ascending = ((a & size) == 0);
+        uint16_t x = perm[a], y = perm[b];
+        bool swap = ascending ? before(y, x) : before(x, y);
+        if (swap) { perm[a] = y; perm[b] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += kFuseThreads) out_order[lo + i] = perm[i];
+}
+
 // RAG2Retriever._apply_safety — one warp per query.
 __global__ void __launch_bounds__(128) safety_kernel(int B, const int32_t* off, const double* rerank,
                                                      const uint8_t* has_rerank, const double* rrf,
@@ -412,6 +468,21 @@ int thr_fuse(thr_handle* h, int variant, int tie_mode, int B, const int64_t* lex
   else fuse_kernel<THR_FUSE_RAG1><<<B, kFuseThreads, 0, s>>>(a);
   thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "fuse_kernel");
+  return THR_OK;
+}
+
+int thr_fuse_ranked(thr_handle* h, int B, const int32_t* off, const int32_t* ranks, const double* weights,
+                    int rrf_k, double* out_rrf, int32_t* out_order, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, B >= 0 && rrf_k >= 0, "thr_fuse_ranked: bad B / rrf_k");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, off && ranks && weights && out_rrf && out_order, "thr_fuse_ranked: NULL argument");
+  const int tok = thr_prof_begin(h, THR_PROF_FUSE, (cudaStream_t)stream);
+  fuse_ranked_kernel<<<B, kFuseThreads, 0, (cudaStream_t)stream>>>(off, ranks, weights, rrf_k, out_rrf, out_order,
+                                                                   h->d_status);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
+  THR_CHECK_LAUNCH(h, "fuse_ranked_kernel");
   return THR_OK;
 }
 

@@ -173,6 +173,20 @@ class Engine:
                                        _ptr(o_ids), _ptr(o_rrf), _ptr(o_rk), _ptr(o_raw), _ptr(o_cnt), self._stream()))
         return o_ids, o_rrf, o_rk, o_raw, o_cnt
 
+    def fuse_ranked(self, off: torch.Tensor, ranks: torch.Tensor, weights: torch.Tensor, rrf_k: int = 60):
+        """RAG2Retriever._fuse_rrf on candidates with ranks: off int32 [B+1], ranks int32 [n,3], weights f64 [B,3]
+        -> rrf [n] f64, order [n] int32 (per query, indices relative to off[q], best first)."""
+        off = self._dev(off, torch.int32, "off")
+        ranks = self._dev(ranks, torch.int32, "ranks")
+        weights = self._dev(weights, torch.float64, "weights")
+        B = off.numel() - 1
+        n = ranks.shape[0]
+        rrf = torch.zeros((max(n, 1),), dtype=torch.float64, device=self.device)
+        order = torch.zeros((max(n, 1),), dtype=torch.int32, device=self.device)
+        self._check(self._lib.thr_fuse_ranked(self._h, B, _ptr(off), _ptr(ranks), _ptr(weights), int(rrf_k),
+                                              _ptr(rrf), _ptr(order), self._stream()))
+        return rrf[:n], order[:n]
+
     def safety(self, off: torch.Tensor, rrf: torch.Tensor, rerank: Optional[torch.Tensor],
                has_rerank: Optional[torch.Tensor], threshold: float, alpha: float, top_k: int):
         """-> keep [n] uint8, refused [B] uint8, max_score [B] f64."""

@@ -26,6 +26,46 @@ from .engine import Engine
 from .index import BM25Index
 
 
+def shard_bounds(n: int, world: int, align: int = 16384) -> list:
+    """Contiguous chunk-id ranges, one per rank; inner boundaries are multiples of `align` (a BM25 doc
+    range) so that a shard's index is a whole number of ranges.  Returns world + 1 offsets."""
+    b = [0]
+    for r in range(1, world):
+        b.append(min(n, (n * r // world) // align * align))
+    b.append(n)
+    return b
+
+
+def exchange_topk(group, world, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, merge_fn):
+    """The one exchange step of the sharded path: every rank contributes its local top-k lists of both
+    channels (ids already global: the kernels add the shard's id_base), one all-gather per array, then
+    merge_fn (K5 on the GPU) reduces G x k -> k per query on every rank, so the fusion runs replicated.
+    merge_fn(scores [G,2B,k] f64, ids [G,2B,k] i64, counts [G,2B] i32, k) -> (scores, ids, counts)."""
+    import torch.distributed as dist
+    dev, G = d_ids.device, world
+    k = max(k_sem, k_lex)
+    sc = torch.full((2, B, k), float("-inf"), dtype=torch.float64, device=dev)
+    ids = torch.full((2, B, k), -1, dtype=torch.int64, device=dev)
+    sc[0, :, :k_sem] = d_sc
+    sc[1, :, :k_lex] = l_sc.to(torch.float64)
+    ids[0, :, :k_sem] = d_ids
+    ids[1, :, :k_lex] = l_ids
+    cnt = torch.stack([d_cnt, l_cnt]).contiguous()
+    g_sc = torch.empty((G, 2 * B, k), dtype=torch.float64, device=dev)
+    g_ids = torch.empty((G, 2 * B, k), dtype=torch.int64, device=dev)
+    g_cnt = torch.empty((G, 2 * B), dtype=torch.int32, device=dev)
+    # flat [G*2B, ...] output views: accepted by NCCL and by gloo (the CPU tests)
+    dist.all_gather_into_tensor(g_sc.view(G * 2 * B, k), sc.view(2 * B, k), group=group)
+    dist.all_gather_into_tensor(g_ids.view(G * 2 * B, k), ids.view(2 * B, k), group=group)
+    dist.all_gather_into_tensor(g_cnt.view(G * 2 * B), cnt.view(2 * B), group=group)
+    m_sc, m_ids, m_cnt = merge_fn(g_sc, g_ids, g_cnt, k)  # dense rows then lexical rows
+    l_ids = m_ids[B:, :k_lex].contiguous()
+    l_sc = m_sc[B:, :k_lex].to(torch.float32)
+    l_sc = torch.where(l_ids < 0, torch.zeros_like(l_sc), l_sc).contiguous()  # thr_bm25_topk pads scores with 0
+    return (m_ids[:B, :k_sem].contiguous(), m_sc[:B, :k_sem].contiguous(), m_cnt[:B].clamp(max=k_sem),
+            l_ids, l_sc, m_cnt[B:].clamp(max=k_lex))
+
+
 @dataclass
 class SearchOutput:
     ids: torch.Tensor        # [B, top_k] int64, -1 padded
@@ -105,26 +145,8 @@ class TripleHybridSearcher:
         return (ids.reshape(-1), off, None)
 
     def _exchange(self, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt):
-        import torch.distributed as dist
-        eng, dev, G = self.engine, self.engine.device, self.world
-        k = max(k_sem, k_lex)
-        sc = torch.full((2, B, k), float("-inf"), dtype=torch.float64, device=dev)
-        ids = torch.full((2, B, k), -1, dtype=torch.int64, device=dev)
-        sc[0, :, :k_sem] = d_sc
-        sc[1, :, :k_lex] = l_sc.to(torch.float64)
-        ids[0, :, :k_sem] = d_ids
-        ids[1, :, :k_lex] = l_ids
-        cnt = torch.stack([d_cnt, l_cnt]).contiguous()
-        g_sc = torch.empty((G, 2 * B, k), dtype=torch.float64, device=dev)
-        g_ids = torch.empty((G, 2 * B, k), dtype=torch.int64, device=dev)
-        g_cnt = torch.empty((G, 2 * B), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(g_sc, sc.view(2 * B, k), group=self.group)
-        dist.all_gather_into_tensor(g_ids, ids.view(2 * B, k), group=self.group)
-        dist.all_gather_into_tensor(g_cnt, cnt.view(2 * B), group=self.group)
-        m_sc, m_ids, m_cnt = eng.merge_topk(g_sc, g_ids, g_cnt, k)  # dense rows then lexical rows
-        return (m_ids[:B, :k_sem].contiguous(), m_sc[:B, :k_sem].contiguous(), m_cnt[:B].clamp(max=k_sem),
-                m_ids[B:, :k_lex].contiguous(), m_sc[B:, :k_lex].to(torch.float32).contiguous(),
-                m_cnt[B:].clamp(max=k_lex))
+        return exchange_topk(self.group, self.world, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt,
+                             self.engine.merge_topk)
 
     # ---- one batch, HOST tensors in / out (the end-to-end path) ----------------------------
     def _pin(self, name: str, like: torch.Tensor) -> torch.Tensor:
