@@ -74,7 +74,8 @@ int64_t thr_launch_count(const thr_handle* h);
 enum {
   THR_PROF_DENSE_SCORE = 0, THR_PROF_DENSE_FINALIZE = 1, THR_PROF_BM25 = 2, THR_PROF_FUSE = 3,
   THR_PROF_MAXSIM = 4, THR_PROF_MERGE = 5, THR_PROF_SAFETY = 6, THR_PROF_BM25_PREP = 7,
-  THR_PROF_SLOTS = 8
+  THR_PROF_DENSE_SEED = 8, /* seed pass of thr_dense_topk: prefix scoring + threshold select (two launches) */
+  THR_PROF_SLOTS = 9
 };
 int thr_prof_enable(thr_handle* h, int on);
 int thr_prof_reset(thr_handle* h);

@@ -18,4 +18,6 @@ for _ in range(5):
     eng.dense_topk(Q, 100, 28)
 p = eng.prof_read()
 ms = p["dense_score"][0] / p["dense_score"][1]
-print(f"N={N} D={D} B={B} dense_score {ms:.3f} ms  {2*B*N*D/ms/1e9:.1f} TFLOP/s  {N*D*2/ms/1e6:.0f} GB/s  finalize {p['dense_finalize'][0]/p['dense_finalize'][1]:.3f} ms")
+seed = p.get("dense_seed", (0.0, 1))
+print(f"N={N} D={D} B={B} dense_score {ms:.3f} ms  {2*B*N*D/ms/1e9:.1f} TFLOP/s  {N*D*2/ms/1e6:.0f} GB/s  "
+      f"finalize {p['dense_finalize'][0]/p['dense_finalize'][1]:.3f} ms  seed(total per call) {seed[0]/5:.3f} ms")

@@ -52,6 +52,21 @@ def test_dense_duplicate_rows_tie_by_id(engine):
     _check(engine, X, Q, 100)
 
 
+def test_dense_seeded_path_large_corpus(engine):
+    """N >= ~0.9M switches on the seed pass (a prefix of the corpus is scored first and its K'-th best
+    score, found by a histogram select, becomes every cluster's initial threshold).  Exact duplicates of a
+    top chunk placed far outside the seed prefix must still come out, in id order."""
+    N, D, B, k = 1_000_000, 64, 12, 100
+    X = synth.dense_rows(0, N, D)
+    X[500_000:500_150] = X[7]
+    X[999_990:] = X[7]
+    Q = synth.dense_queries(B, D, X, n_plant=50_000)
+    Q[0] = X[7]
+    Q[1] = X[123_456]
+    gap = _check(engine, X, Q, k)
+    assert (gap > 0).all()
+
+
 def test_dense_single_cta_path_agrees():
     """THR_DENSE_CTA_GROUP=1 (M=128 single-CTA MMA) must give the same answer as the CTA-pair path."""
     if not torch.cuda.is_available():

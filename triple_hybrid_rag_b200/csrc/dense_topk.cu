@@ -36,6 +36,7 @@ constexpr int kCap = 1024;         // candidate slots per (cluster, query); raw 
 constexpr int kMaxSel = 256;       // largest K' = k + margin
 constexpr int kScoreThreads = 192;
 constexpr int kFinalThreads = 256;
+constexpr int kSeedTiles = 3;      // tiles per cluster in the seed pass: 3 x 256 candidates fit a list without compaction
 
 template <int G> struct ScoreCfg {
   static constexpr int kStages = (G == 2) ? 7 : 4;
@@ -55,6 +56,8 @@ struct ScoreArgs {
   int Bpad;         // row stride of cand/cnt
   uint64_t* cand;   // [n_clusters][Bpad][kCap]
   int32_t* cnt;     // [n_clusters][Bpad]
+  const float* tau_init;  // [Bpad] nullable: per-query lower bound of the K'-th best score (seed pass)
+  int seed_mode;          // seed pass: leave the lists uncompacted (<= kSeedTiles * kTileN entries each)
   thr_dev_status* status;
 };
 
@@ -224,6 +227,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // lane issues the tcgen05 instructions.  Descriptors are precomputed: stage s adds
     // s * (stage bytes >> 4) to the 14-bit start-address field, K-step k adds 2 (32 bytes).
     if (leader) {
+      const bool issuer = elect_one();  // one lane issues; elect.sync lets the compiler emit plain uniform code
       constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM * G, kTileN);
       constexpr uint32_t kStageDescStep = (uint32_t)Cfg::kStageBytes >> 4;
       const uint64_t adesc0 = umma_desc_sw128(a_smem(0));
@@ -239,7 +243,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(full_bar(stage), phase, a.status, 201);
             tc_fence_after_sync();
-            if (lane == 0) {
+            if (issuer) {
               const uint64_t adesc = adesc0 + (uint64_t)(stage * kStageDescStep);
               const uint64_t bdesc = bdesc0 + (uint64_t)(stage * kStageDescStep);
 #ifndef THR_DBG_NO_MMA
@@ -256,7 +260,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             __syncwarp();
             if (++stage == (uint32_t)Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
-          if (lane == 0) {
+          if (issuer) {
             if (G == 2) umma_commit_pair_mcast(tfull_bar(acc), 0x3);
             else umma_commit_1cta(tfull_bar(acc));
           }
@@ -273,7 +277,9 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const int row = qb * qrows + (int)rank * kBlockM + (int)lane_base + (int)lane;  // query index
       const bool row_valid = row < a.B;
       uint64_t* rowbuf = a.cand + ((size_t)cluster_id * a.Bpad + (row_valid ? row : 0)) * kCap;
-      float tau = row_valid ? -CUDART_INF_F : CUDART_INF_F;  // padding rows of the query block never pass
+      // padding rows of the query block never pass; a seeded threshold is a valid lower bound of the
+      // global K'-th best score, so nothing that could reach the final top-k is filtered
+      float tau = row_valid ? (a.tau_init ? a.tau_init[row] : -CUDART_INF_F) : CUDART_INF_F;
       int cnt = 0;
       for (int64_t t = tile_lo; t < tile_hi && ok; ++t, ++tcount) {
         const int acc = tcount & 1;
@@ -359,7 +365,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
       }
       // final compaction of this query block: every list ends with <= K' entries
-      unsigned need = __ballot_sync(0xffffffffu, row_valid && cnt > a.ksel);
+      unsigned need = __ballot_sync(0xffffffffu, row_valid && cnt > a.ksel && !a.seed_mode);
       while (need) {
         const int src = __ffs(need) - 1;
         need &= need - 1;
@@ -458,7 +464,6 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
     }
     T = s_prefix;
   }
-
   // 3. collect survivors
   for (int i = tid; i < m; i += kFinalThreads) {
     const uint64_t key = keys[i];
@@ -524,6 +529,75 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Seed select: a lower bound of each query's corpus-wide K'-th best score from the (uncompacted) lists of
+// the seed pass.  Two-level histogram over the orderable score bits (12 + 8 bits): tau = lower edge of the
+// bin in which the running count from the top reaches K', one ulp lower so that the filter's strict ">"
+// keeps ties.  At least K' sample chunks score above tau, so the corpus-wide K'-th best does too.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_seed_select_kernel(const uint64_t* cand, const int32_t* cnt,
+                                                                int n_clusters, int Bpad, int ksel, float* tau_out) {
+  __shared__ uint32_t hist[4096];
+  __shared__ uint32_t part[256];
+  __shared__ uint32_t s_bin, s_above;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t prefix = 0, above = 0;
+  bool enough = true;
+  for (int level = 0; level < 2 && enough; ++level) {
+    const int nb = level == 0 ? 4096 : 256;
+    for (int i = tid; i < nb; i += 256) hist[i] = 0;
+    __syncthreads();
+    for (int c = warp; c < n_clusters; c += 8) {
+      const int n = min(cnt[(size_t)c * Bpad + q], kCap);
+      const uint64_t* src = cand + ((size_t)c * Bpad + q) * kCap;
+      for (int i = lane; i < n; i += 32) {
+        const uint32_t o = f32_orderable(__uint_as_float((uint32_t)(src[i] >> 32)));
+        if (level == 0) atomicAdd(&hist[o >> 20], 1u);
+        else if ((o >> 20) == prefix) atomicAdd(&hist[(o >> 12) & 255u], 1u);
+      }
+    }
+    __syncthreads();
+    // suffix sums: thread t owns bins [t*per, (t+1)*per); find the bin where the count from the top reaches ksel
+    const int per = nb / 256;
+    uint32_t mine = 0;
+    for (int j = 0; j < per; ++j) mine += hist[tid * per + j];
+    part[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t cum = above;
+      int t = 255;
+      for (; t >= 0; --t) {
+        if (cum + part[t] >= (uint32_t)ksel) break;
+        cum += part[t];
+      }
+      if (t < 0) { s_bin = 0xffffffffu; s_above = cum; }
+      else {
+        int b = t * per + per - 1;
+        for (; b > t * per; --b) {
+          if (cum + hist[b] >= (uint32_t)ksel) break;
+          cum += hist[b];
+        }
+        s_bin = (uint32_t)b;
+        s_above = cum;
+      }
+    }
+    __syncthreads();
+    if (s_bin == 0xffffffffu) enough = false;  // fewer than K' candidates in total
+    else if (level == 0) prefix = s_bin;
+    else prefix = (prefix << 8) | s_bin;
+    above = s_above;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float t = -CUDART_INF_F;
+    if (enough) {
+      const uint32_t edge = prefix << 12;  // 20 significant bits of the orderable score
+      t = f32_from_orderable(edge > 0 ? edge - 1u : 0u);
+    }
+    tau_out[q] = t;
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -544,7 +618,7 @@ void thr_dense_state_free(thr_handle* h) {
 
 template <int G>
 static int launch_score(thr_handle* h, const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int prof_slot = THR_PROF_DENSE_SCORE) {
   using Cfg = ScoreCfg<G>;
   THR_CUDA(h, cudaFuncSetAttribute(dense_score_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
@@ -560,7 +634,7 @@ static int launch_score(thr_handle* h, const CUtensorMap& mq, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const int tok = thr_prof_begin(h, THR_PROF_DENSE_SCORE, stream);
+  const int tok = thr_prof_begin(h, prof_slot, stream);
   THR_CUDA(h, cudaLaunchKernelEx(&cfg, dense_score_kernel<G>, mq, mx, a));
   thr_prof_end(h, tok, stream);
   h->launches++;
@@ -607,7 +681,7 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64
   const int Bpad = (B + 255) & ~255;
   const size_t cand_bytes = (size_t)n_clusters * Bpad * kCap * sizeof(uint64_t);
   const size_t cnt_bytes = (size_t)n_clusters * Bpad * sizeof(int32_t);
-  uint8_t* ws = (uint8_t*)thr_scratch(h, cand_bytes + cnt_bytes);
+  uint8_t* ws = (uint8_t*)thr_scratch(h, cand_bytes + cnt_bytes + (size_t)Bpad * sizeof(float));
   if (!ws) return THR_ENOMEM;
 
   CUtensorMap map_q;
@@ -617,9 +691,9 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64
   ScoreArgs a;
   a.B = B; a.N = st->N; a.D = st->D; a.ksel = k + margin; a.n_clusters = n_clusters; a.Bpad = Bpad;
   a.cand = (uint64_t*)ws; a.cnt = (int32_t*)(ws + cand_bytes); a.status = h->d_status;
-  THR_CUDA(h, cudaMemsetAsync(a.cnt, 0, cnt_bytes, s));
-  rc = (G == 2) ? launch_score<2>(h, map_q, st->map_x, a, s) : launch_score<1>(h, map_q, st->map_x, a, s);
-  if (rc != THR_OK) return rc;
+  a.tau_init = nullptr;
+  a.seed_mode = 0;
+  float* tau_seed = (float*)(ws + cand_bytes + cnt_bytes);
 
   FinalArgs f;
   f.Q = (const __nv_bfloat16*)Q; f.X = (const __nv_bfloat16*)st->X; f.B = B; f.D = st->D; f.N = st->N;
@@ -628,6 +702,30 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64
   f.out_count = out_count; f.out_gap = out_gap;
   const size_t fsmem = (size_t)n_clusters * f.ksel * sizeof(uint64_t) + (size_t)st->D * 2;
   THR_CUDA(h, cudaFuncSetAttribute(dense_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+
+  // Seed pass: score a small prefix of the corpus first and start the full pass from its K'-th best
+  // score.  Every cluster then filters with a threshold learnt from ~130k chunks from its first tile on
+  // (instead of from -inf), which cuts the epilogue's append work and list compactions several-fold.
+  const int64_t seed_rows = (int64_t)n_clusters * kSeedTiles * kTileN;
+  const char* noseed = getenv("THR_DENSE_NO_SEED");
+  if (st->N >= 16 * seed_rows && !(noseed && noseed[0] == '1')) {
+    ScoreArgs sa = a;
+    sa.N = seed_rows;
+    sa.seed_mode = 1;
+    THR_CUDA(h, cudaMemsetAsync(a.cnt, 0, cnt_bytes, s));
+    rc = (G == 2) ? launch_score<2>(h, map_q, st->map_x, sa, s, THR_PROF_DENSE_SEED)
+                  : launch_score<1>(h, map_q, st->map_x, sa, s, THR_PROF_DENSE_SEED);
+    if (rc != THR_OK) return rc;
+    const int tok0 = thr_prof_begin(h, THR_PROF_DENSE_SEED, s);
+    dense_seed_select_kernel<<<B, 256, 0, s>>>(a.cand, a.cnt, n_clusters, Bpad, k + margin, tau_seed);
+    thr_prof_end(h, tok0, s);
+    THR_CHECK_LAUNCH(h, "dense_seed_select_kernel");
+    a.tau_init = tau_seed;
+  }
+  THR_CUDA(h, cudaMemsetAsync(a.cnt, 0, cnt_bytes, s));
+  rc = (G == 2) ? launch_score<2>(h, map_q, st->map_x, a, s) : launch_score<1>(h, map_q, st->map_x, a, s);
+  if (rc != THR_OK) return rc;
+
   const int tok = thr_prof_begin(h, THR_PROF_DENSE_FINALIZE, s);
   dense_finalize_kernel<<<B, kFinalThreads, fsmem, s>>>(f);
   thr_prof_end(h, tok, s);
