@@ -24,7 +24,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "QPS (batch 256) triple-hybrid top-100 over 10M x 1536 chunks"
-ALIGN = 16384  # shard boundaries are BM25 block boundaries
+ALIGN = 16384  # shard boundaries (a multiple of the BM25 range size)
+BM25_BLK = 2048  # docs per BM25 range
 GEN_DOCS = 262144
 
 
@@ -53,46 +54,61 @@ def peaks():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML getters on a
+    thread (nvidia_ml_py): a looping `nvidia-smi --query-gpu` was measured to stall the timed loop by
+    several ms per step on this driver, the three NVML getters used here do not."""
+    PERIOD_S = 0.02
 
     def __init__(self, index: int):
-        self.proc = None
         self.index = index
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = None
+        self._thread = None
 
     def start(self):
+        if os.environ.get("THR_BENCH_NO_CLOCKS"):
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self._stop = threading.Event()
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for n, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    self._stop.wait(self.PERIOD_S)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
+
+    def mark(self):
+        """Drop what was sampled so far (call right before the timed region)."""
+        self.sm.clear()
+        self.reasons.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "NVML getters every 20 ms"}
 
 
 def make_config(args, world: int):
@@ -212,7 +228,7 @@ def main():
             m = (doc >= a - g_lo) & (doc < b - g_lo)
             doc, term, tf = doc[m] - (a - g_lo), term[m], tf[m]
             L = L[a - g_lo:b - g_lo]
-        parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=ALIGN, avgdl=avgdl,
+        parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=BM25_BLK, avgdl=avgdl,
                                      idf=torch.zeros(V), n_docs_global=N))
         del doc, term, tf, L
     df = sum(p.df for p in parts)
@@ -245,7 +261,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timed loop ----
-    eng.prof_enable(True)  # per-kernel event pairs; created before the warm-up so the timed region has no one-offs
+    if not os.environ.get("THR_BENCH_NO_PROF"):
+        eng.prof_enable(True)  # per-kernel event pairs; created before the warm-up so the timed region has no one-offs
     clocks = ClockSampler(local)
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -13,7 +13,7 @@ G = 262144
 for gb in range((N + G - 1) // G):
     rows = min(G, N - gb * G)
     doc, term, tf, L = synth.bm25_block_coo(gb, rows, V=V, device=dev)
-    parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=16384, avgdl=200.0, n_docs_global=N))
+    parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=2048, avgdl=200.0, n_docs_global=N))
 idx = BM25Index.concat(parts) if len(parts) > 1 else parts[0]
 eng.bm25_index_set(idx.skip, idx.postings, idx.idf, idx.n_docs, idx.blk_docs, idx.V)
 qs = synth.bm25_queries(B, V=V)

@@ -31,8 +31,8 @@ def _check(engine, idx, orc, queries, k, id_base=0):
     assert np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
 
 
-@pytest.mark.parametrize("n_docs,V,blk,B,k", [(20_000, 5_000, 4096, 64, 100), (50_000, 20_000, 16384, 128, 100),
-                                              (3_000, 500, 1024, 17, 10)])
+@pytest.mark.parametrize("n_docs,V,blk,B,k", [(20_000, 5_000, 1024, 64, 100), (50_000, 20_000, 2048, 128, 100),
+                                              (3_000, 500, 256, 17, 10)])
 def test_bm25_matches_oracle(engine, n_docs, V, blk, B, k):
     idx, orc = _corpus(n_docs, V, blk)
     qs = synth.bm25_queries(B, V=V, min_rank=min(100, V // 10))
@@ -40,16 +40,16 @@ def test_bm25_matches_oracle(engine, n_docs, V, blk, B, k):
 
 
 def test_bm25_heavy_terms_split_stages_and_edge_queries(engine):
-    """Head terms (df ~ n_docs) overflow a ring stage and the candidate list: exercises the split
-    steps and the mid-range compaction; also empty, unknown-term and duplicate-term queries."""
-    idx, orc = _corpus(40_000, 2_000, 16384)
+    """Head terms (df ~ n_docs) fill the candidate list within one round: exercises the overflow roll-back
+    with its serial redo and the compactions; also empty, unknown-term and duplicate-term queries."""
+    idx, orc = _corpus(40_000, 2_000, 2048)
     qs = [[0, 1, 2, 3, 4, 5, 6, 7], [0], [1999], [], [5000, -3], [10, 10, 11], [3, 700, 1500], list(range(32))]
     _check(engine, idx, orc, qs, 256)
     _check(engine, idx, orc, qs, 1, id_base=123456789)
 
 
 def test_bm25_fp32_within_tolerance_of_fp64(engine):
-    idx, orc = _corpus(20_000, 5_000, 4096)
+    idx, orc = _corpus(20_000, 5_000, 1024)
     qs = synth.bm25_queries(16, V=5_000)
     _, s32, cnt = ob.bm25_topk(orc, qs, 100)
     for q, s, c in zip(qs, s32, cnt):

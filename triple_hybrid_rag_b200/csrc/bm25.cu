@@ -12,22 +12,21 @@
 // a term) and skip[t * n_blk + r] = first posting of term t whose doc lies in range r (blk_docs docs).
 //
 // One CTA works on one unit (a query restricted to a span of doc ranges; heavy queries are cut into
-// several units) at a time, walking the span range by range with fp32 accumulators for one range in
-// shared memory.  Two warp roles, asynchronous to each other through mbarriers:
-//   producer (1 warp)  per range: reads the query terms' skip entries (prefetched 12 ranges ahead with
-//                      cp.async), packs the terms' posting segments into one step, allocates room in a
-//                      96 KB ring and moves the segments global -> shared with cp.async.bulk.
-//   consumers          per step, term by term: one coalesced pass shared -> accumulator (doc ids are
-//                      unique inside a posting list and terms are separated by a named barrier => no
-//                      atomics).  The posting that touches an accumulator first marks itself as the
-//                      doc's owner (bit 31 of the staged doc id); one more pass over the staged postings
-//                      lets every owner read its doc's final score, append it to the candidate list if
-//                      it beats the running threshold and re-zero the slot, so the work per range is
-//                      proportional to its postings, not to blk_docs.  A range too large for one step
-//                      falls back to a scan of the accumulators.
-// The barrier after a range's last term doubles as the capacity vote (bar.red.or): when the candidate
-// list could overflow it is compacted to the best k by a radix select, which also raises the threshold.
-// The per-step code is kept to ~150 instructions per thread: the kernel is issue-bound, not DRAM-bound.
+// several units) at a time.  The kernel is issue-bound, not DRAM-bound (a query touches ~13% of the docs, so
+// a range of 2048 docs carries only a few hundred postings): what matters is the number of instructions
+// per posting.  Therefore every warp is autonomous: it OWNS whole ranges — a contiguous run of the unit's
+// ranges, with a private 2048-slot fp32 accumulator in shared memory — and does everything for them:
+//   * reads the terms' skip entries (lane t <-> query term t, loaded two ranges ahead),
+//   * loads the terms' posting segments straight from global memory, coalesced; the first 32 postings of
+//     each of the first 8 terms are prefetched into registers one range ahead, so DRAM latency overlaps the
+//     previous range's arithmetic,
+//   * accumulates term by term in query order (__syncwarp between terms: no atomics, no block barriers),
+//   * re-walks the postings, takes each touched doc's final score once, re-zeroes the slot and appends the
+//     score to the CTA's candidate list if it beats the running threshold tau.
+// The 16 warps of a CTA only meet at round boundaries (a round = 1..8 ranges per warp): there the
+// candidate list is compacted to the best k by a radix select when it is half full (which raises tau).
+// An append that would overflow the list raises a flag instead; the round is then rolled back and redone
+// serially with compactions in between (cannot overflow: one range appends at most 2048 <= cap - k).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -35,39 +34,20 @@
 namespace {
 
 constexpr int kMaxTerms = 32;
-#ifndef THR_BM25_CW
-#define THR_BM25_CW 16
-#endif
-constexpr int kConsumerWarps = THR_BM25_CW;
-constexpr int kConsumers = kConsumerWarps * 32;                    // 512
-constexpr int kThreads = kConsumers + 32;                          // + producer warp
-constexpr int kMaxBlkDocs = 16384;
-constexpr int kRingCap = 12288;                  // postings in the ring (96 KB)
-constexpr int kStepCap = 4096;                   // postings per step
-constexpr int kSlots = 8;                        // steps in flight
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;            // 512
+constexpr int kConsumers = kThreads;
+constexpr int kMaxBlkDocs = 2048;                // docs per range = accumulator slots per warp
 constexpr int kMaxSelB = 256;
-constexpr int kCandCap = kStepCap + 2 * kMaxSelB;  // a single-step range can append a whole step after a compaction
-constexpr int kMaxSeg = kMaxTerms;               // one segment per term and step
-constexpr int kPtrDepth = 12;                    // skip entries prefetched ahead
-constexpr int kPtrRing = 16;
+constexpr int kCandCap = 4608;                   // >= kMaxBlkDocs + 2 * kMaxSelB
+constexpr int kFast = 8;                         // term slots with register-prefetched first chunks
+constexpr int kMaxRound = 8;                     // ranges per warp and round, at most
 
 struct Posting { uint32_t doc; float imp; };
 
 // A work unit: one query restricted to the doc ranges [r0, r1).
 struct Unit { int q; int r0; int r1; unsigned cost; };
 constexpr int kMaxUnitsPerQuery = 16;
-
-enum { kLast = 1, kEou = 2, kSingle = 4 };
-
-struct StepMeta {
-  int nseg;
-  int flags;             // kLast: last step of its range; kSingle: the only step of its range; kEou: end of unit
-  int range;             // range index
-  int add_bound;         // upper bound of docs the range can append (valid on the last step)
-  uint2 seg[kMaxSeg];    // .x = first valid posting (ring index) | count << 16,  .y = idf of the term (float bits)
-};
-static_assert(kRingCap <= 65536 && kStepCap < 65536, "segment start / count are packed into 16 bits each");
-static_assert(sizeof(StepMeta) % 8 == 0, "mbarriers follow the metadata and need 8-byte alignment");
 
 struct Bm25Args {
   const int64_t* skip;    // [V * n_blk + 1]
@@ -87,40 +67,15 @@ struct Bm25Args {
   thr_dev_status* status;
 };
 
-__device__ __forceinline__ void bar_consumers() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
-}
-// Barrier over the consumer threads that also ORs a predicate: every thread gets the same answer.
-__device__ __forceinline__ bool bar_consumers_or(bool p) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 p, %1, 0;\n\t"
-      "bar.red.or.pred q, 1, %2, p;\n\t"
-      "selp.u32 %0, 1, 0, q;\n\t}"
-      : "=r"(r)
-      : "r"((uint32_t)p), "n"(kConsumers)
-      : "memory");
-  return r != 0;
+__device__ __forceinline__ void bar_consumers() { __syncthreads(); }
+
+__device__ __forceinline__ uint2 ldg_posting(const Posting* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
 }
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      :
-      : "r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// Block-cooperative (consumer threads only): keep the ksel largest of keys[0..n) in place, n > ksel.
+// Block-cooperative: keep the ksel largest of keys[0..n) in place, n > ksel.
 // Returns the ksel-th largest key.  hist/scal are shared scratch.
 __device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t* hist,
                                        unsigned long long* s_prefix, int* s_want, int* s_cnt, int tid) {
@@ -165,52 +120,28 @@ __device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t
   return T;
 }
 
-constexpr size_t kSmemRing = (size_t)kRingCap * sizeof(Posting);
-constexpr size_t kSmemAcc = (size_t)kMaxBlkDocs * 4;
+constexpr size_t kSmemAcc = (size_t)kWarps * kMaxBlkDocs * 4;
 constexpr size_t kSmemCand = (size_t)kCandCap * 8;
-constexpr size_t kSmemMeta = (size_t)kSlots * sizeof(StepMeta);
-constexpr size_t kSmemBars = (size_t)2 * kSlots * 8;
-constexpr size_t kSmemPtr = (size_t)kPtrRing * 32 * 8;
 constexpr size_t kSmemMisc = 256 * 4 + kMaxTerms * 8 + 8 + 8 * 4;
-constexpr size_t kBm25Smem = kSmemRing + kSmemAcc + kSmemCand + kSmemMeta + kSmemBars + kSmemPtr + kSmemMisc + 256;
+constexpr size_t kBm25Smem = kSmemAcc + kSmemCand + kSmemMisc + 256;
 
 __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  // carve-up (every region keeps 8-byte alignment)
-  Posting* ring = (Posting*)gen;
-  float* acc = (float*)(gen + kSmemRing);
-  uint64_t* cand = (uint64_t*)(acc + kMaxBlkDocs);
-  StepMeta* meta = (StepMeta*)(cand + kCandCap);
-  uint64_t* bars = (uint64_t*)(meta + kSlots);                                // full, empty
-  long long* pring = (long long*)(bars + 2 * kSlots);                         // [kPtrRing][32]
-  uint32_t* hist = (uint32_t*)(pring + kPtrRing * 32);                        // 256
+  float* acc = (float*)gen;                                                    // [kWarps][kMaxBlkDocs]
+  uint64_t* cand = (uint64_t*)(acc + kWarps * kMaxBlkDocs);                    // kCandCap
+  uint32_t* hist = (uint32_t*)(cand + kCandCap);                              // 256
   int* q_term = (int*)(hist + 256);                                           // kMaxTerms
   float* q_idf = (float*)(q_term + kMaxTerms);                                // kMaxTerms
   unsigned long long* s_prefix = (unsigned long long*)(q_idf + kMaxTerms);
-  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=unit [4]=nterms
+  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=unit [4]=nterms [5]=overflow
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
-  auto empty_bar = [&](int s) { return smem_u32(&bars[kSlots + s]); };
-
-  if (tid == 0) {
-    for (int s = 0; s < kSlots; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), kConsumerWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < kMaxBlkDocs; i += kThreads) acc[i] = 0.f;
-  __syncthreads();
-
-  uint32_t it = 0;  // step counter, advances identically in all three roles
-  const int R = a.blk_docs;
-  // producer-only ring state
-  int head = 0;          // next free posting in the ring
-  uint32_t oldest = 0;   // oldest step whose data may still be in use
-  int my_begin = 0;      // lane j < kSlots: ring offset of the step in slot j
+  for (int i = tid; i < kWarps * kMaxBlkDocs; i += kThreads) acc[i] = 0.f;
+  const uint32_t accw = smem_u32(acc) + (uint32_t)warp * kMaxBlkDocs * 4u;   // this warp's accumulator
+  volatile int* v_cnt = &s_int[2];
+  volatile int* v_ovf = &s_int[5];
 
   for (;;) {
     // ---- fetch the next unit (whole CTA) ----
@@ -236,275 +167,240 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       }
       q_term[tid] = t;
       q_idf[tid] = w;
-      if (tid == 0) { s_int[4] = nt; s_int[2] = 0; }
+      if (tid == 0) { s_int[4] = nt; s_int[2] = 0; s_int[5] = 0; }
     }
     __syncthreads();
     const int nterms = s_int[4];
 
-    if (warp == kConsumerWarps) {
-      // ======================= producer warp =======================
-      const int my_term = lane < nterms ? q_term[lane] : -1;
-      const float my_idf = lane < nterms ? q_idf[lane] : 0.f;
-      const int64_t* row = a.skip + (size_t)(my_term < 0 ? 0 : my_term) * a.n_blk + r_begin;
-      const int n_ranges = r_end - r_begin;
-      const uint32_t my_pr = smem_u32(pring + lane);
-      auto issue_ptr = [&](int e) {  // skip entry e of this unit: row[e], e in [0, n_ranges]
-        if (my_term >= 0 && e <= n_ranges) cp_async_8(my_pr + (uint32_t)(e % kPtrRing) * 256u, row + e);
-        cp_async_commit();
-      };
-      auto wait_step = [&](uint32_t j) {  // until the consumers released step j
-        mbar_wait_relaxed(empty_bar(j % kSlots), (j / kSlots) & 1u, a.status, 400);
-      };
-      // Room for n postings (even) in the ring for step `it`; returns the ring offset.
-      auto alloc = [&](int n) -> int {
-        while (oldest + kSlots <= it) { wait_step(oldest); ++oldest; }  // the slot itself must be free
-        for (;;) {
-          int pos = -1;
-          if (oldest == it) { head = 0; pos = 0; }  // nothing outstanding
-          else {
-            const int tb = __shfl_sync(0xffffffffu, my_begin, (int)(oldest % kSlots));
-            if (head >= tb) {            // occupied: [tb, head)
-              if (n <= kRingCap - head) pos = head;
-              else if (n < tb) pos = 0;
-            } else if (n < tb - head) {  // occupied: [tb, cap) + [0, head)
-              pos = head;
-            }
-          }
-          if (pos >= 0) {
-            head = pos + n;
-            if (lane == (int)(it % kSlots)) my_begin = pos;
-            return pos;
-          }
-          wait_step(oldest);
-          ++oldest;
-        }
-      };
+    // this warp's contiguous run of ranges
+    const int n_ranges = r_end - r_begin;
+    const int per_warp = (n_ranges + kWarps - 1) / kWarps;        // same for every warp: the round loop is uniform
+    const int my_r0 = min(r_end, r_begin + warp * per_warp);
+    const int my_n = min(r_end, my_r0 + per_warp) - my_r0;
+    const int my_term = lane < nterms ? q_term[lane] : -1;
+    const float my_w = lane < nterms ? q_idf[lane] : 0.f;
+    const int64_t* row = a.skip + (size_t)(my_term < 0 ? 0 : my_term) * a.n_blk;  // lane t <-> query term t
+    float tau = 0.f;  // only score > 0 is eligible; raised by compactions
 
-      for (int e = 0; e <= kPtrDepth; ++e) issue_ptr(e);
-      for (int i = 0; i < n_ranges; ++i) {
-        issue_ptr(i + kPtrDepth + 1);
-        cp_async_wait<kPtrDepth>();  // entries 0 .. i+1 have landed
-        int64_t lo = 0, hi = 0;
-        if (my_term >= 0) {
-          lo = pring[(i % kPtrRing) * 32 + lane];
-          hi = pring[((i + 1) % kPtrRing) * 32 + lane];
-        }
-        int64_t remaining = hi - lo;
-        long long tot = remaining;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
-        if (tot == 0) continue;  // nothing in this range for this query
-        const int add_bound = (int)min((long long)R, tot);
-        bool first_step = true;
-        // Pack the terms' segments into steps of <= kStepCap postings, in term order (normally one step).
-        for (;;) {
-          const bool has = remaining > 0;
-          const int slack = (int)(lo & 1);  // copies start at an even posting (16-byte granules)
-          const long long need_ll = has ? ((slack + remaining + 1) & ~1LL) : 0;
-          const int need = (int)min(need_ll, (long long)(kStepCap + 2));
-          int incl = need;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-          }
-          const int before = incl - need;
-          int take = 0, cp = 0;
-          if (has) {
-            if (incl <= kStepCap) { take = (int)remaining; cp = need; }
-            else if (before < kStepCap) {  // first term that does not fit: take a piece if it is worth a copy
-              const int room = kStepCap - before - slack - 1;
-              if (room >= 64) { take = (int)min((long long)room, (long long)remaining); cp = (slack + take + 1) & ~1; }
-            }
-          }
-          int cincl = cp;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, cincl, d);
-            if (lane >= d) cincl += v;
-          }
-          const int total_cp = __shfl_sync(0xffffffffu, cincl, 31);
-          const int off = cincl - cp;
-          const unsigned have = __ballot_sync(0xffffffffu, take > 0);
-          const unsigned still = __ballot_sync(0xffffffffu, remaining - take > 0);
-          const int s = it % kSlots;
-          const int pos = alloc(total_cp);
-          if (take > 0) {
-            const int g = __popc(have & ((1u << lane) - 1));
-            meta[s].seg[g] = make_uint2((uint32_t)(pos + off + slack) | ((uint32_t)take << 16), __float_as_uint(my_idf));
-          }
-          __syncwarp();
-          if (lane == 0) {
-            meta[s].nseg = __popc(have);
-            meta[s].flags = (still ? 0 : kLast) | ((first_step && !still) ? kSingle : 0);
-            meta[s].range = r_begin + i;
-            meta[s].add_bound = add_bound;
-            // metadata is written with generic stores; the arrive has release semantics
-            mbar_arrive_expect_tx(full_bar(s), (uint32_t)total_cp * 8u);
-          }
-          __syncwarp();
-          if (take > 0)
-            bulk_g2s(smem_u32(ring + pos + off), a.post + (lo - slack), (uint32_t)cp * 8u, full_bar(s));
-          lo += take;
-          remaining -= take;
-          first_step = false;
-          ++it;
-          if (!still) break;
-        }
-      }
-      // end-of-unit marker
-      {
-        const int s = it % kSlots;
-        (void)alloc(0);
-        if (lane == 0) {
-          meta[s].nseg = 0;
-          meta[s].flags = kEou;
-          mbar_arrive(full_bar(s));
-        }
-        ++it;
-        __syncwarp();
-      }
-      cp_async_wait<0>();
-    } else {
-      // ======================= consumers =======================
-      // The hot loops address shared memory with 32-bit shared-space addresses (ld/st.shared).
-      float tau = 0.f;  // only score > 0 is eligible; raised by compactions
-      volatile int* v_cnt = &s_int[2];
-      const uint32_t ring_addr = smem_u32(ring), acc_addr = smem_u32(acc);
-      // rare path: one candidate per calling lane
-      auto emit1 = [&](float v, uint32_t doc) {
-        const int pos = atomicAdd(&s_int[2], 1);
-        if (pos < kCandCap) cand[pos] = pack_key(v, doc);
-        else dev_report(a.status, THR_EOVERFLOW, 430, pos);  // excluded by the capacity votes; keep it loud
-      };
-      auto compact = [&]() {
-        const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-        tau = key_score(T);
-        if (tid == 0) s_int[2] = s_int[1];
-        bar_consumers();
-      };
-      for (;;) {
-        const int s = it % kSlots;
-        const uint32_t ph = (it / kSlots) & 1u;
-        mbar_wait(full_bar(s), ph, a.status, 410);
-        ++it;
-        const uint32_t meta_addr = smem_u32(&meta[s]);
-        int nseg, flags, range, add_bound;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(nseg), "=r"(flags), "=r"(range), "=r"(add_bound) : "r"(meta_addr));
-        if (flags & kEou) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_bar(s));
-          break;
-        }
-        const uint32_t doc0 = (uint32_t)range << a.blk_shift;
-        const uint32_t acc0 = acc_addr - doc0 * 4u;  // &acc[doc - doc0] == acc0 + doc * 4 (mod 2^32)
-        const bool single = (flags & kSingle) != 0;
-        const bool last = (flags & kLast) != 0;
-        // tight: even a list compacted to k could overflow (only ranges spread over several steps) — those
-        // vote per scan chunk instead.  Otherwise a true vote implies count > k, which the compaction needs.
-        const bool tight = a.k + add_bound > kCandCap;
-        bool vote = false;
-        // ---- pass 1: accumulate, one term at a time ----
-        uint32_t seg_addr = meta_addr + 16u;
-        for (int g = 0; g < nseg; ++g, seg_addr += 8u) {
-          uint32_t pw;
-          float w;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(pw), "=f"(w) : "r"(seg_addr));
-          const uint32_t end = ring_addr + ((pw & 0xffffu) + (pw >> 16)) * 8u;
-          for (uint32_t pa = ring_addr + ((pw & 0xffffu) + (uint32_t)tid) * 8u; pa < end; pa += kConsumers * 8u) {
-            uint32_t doc;
-            float imp, old;
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(doc), "=f"(imp) : "r"(pa));
-            const uint32_t aa = acc0 + doc * 4u;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old) : "r"(aa));
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(__fadd_rn(old, __fmul_rn(w, imp))) : "memory");
-            // the first posting to touch a doc owns it in pass 2
-            if (single && old == 0.f) asm volatile("st.shared.b32 [%0], %1;" ::"r"(pa), "r"(doc | 0x80000000u) : "memory");
-          }
-          // term boundary: the next term (or the next step) may hit the same docs
-          if (g + 1 == nseg && last && !tight) vote = bar_consumers_or(*v_cnt + add_bound > kCandCap);
-          else bar_consumers();
-        }
-        if (!single) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_bar(s));  // this warp no longer reads the step's postings
-        }
-        if (!last) continue;
-
-        // ---- range complete: collect its docs ----
-        if (vote) compact();
-        if (single) {
-          // sparse: owners read the final score, append if > tau, re-zero the slot
-          seg_addr = meta_addr + 16u;
-          for (int g = 0; g < nseg; ++g, seg_addr += 8u) {
-            uint32_t pw;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pw) : "r"(seg_addr));
-            const uint32_t end = ring_addr + ((pw & 0xffffu) + (pw >> 16)) * 8u;
-            for (uint32_t pa = ring_addr + ((pw & 0xffffu) + (uint32_t)tid) * 8u; pa < end; pa += kConsumers * 8u) {
-              uint32_t d;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(d) : "r"(pa));
-              if (d & 0x80000000u) {
-                const uint32_t doc = d & 0x7fffffffu;
-                const uint32_t aa = acc0 + doc * 4u;
-                float v;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(aa));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(0.f) : "memory");
-                if (v > tau) emit1(v, doc);
-              }
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_bar(s));
-        } else {
-          // the range came in several steps: scan the accumulators
-          for (int c0 = 0; c0 < R; c0 += kConsumers * 4) {  // uniform trip count: the vote is a block barrier
-            if (tight && bar_consumers_or(*v_cnt + kConsumers * 4 > kCandCap)) compact();
-            const int c = c0 + tid * 4;
-            if (c < R) {
-              float4* p4 = reinterpret_cast<float4*>(&acc[c]);
-              const float4 v = *p4;
-              if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-                *p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint32_t d = doc0 + (uint32_t)c;
-                if (v.x > tau) emit1(v.x, d);
-                if (v.y > tau) emit1(v.y, d + 1);
-                if (v.z > tau) emit1(v.z, d + 2);
-                if (v.w > tau) emit1(v.w, d + 3);
-              }
-            }
-          }
-        }
-        bar_consumers();  // slots re-zeroed and appends visible before the next range accumulates
-      }
-
-      // ---- end of unit: final top-k, sorted ----
+    // rare path: one candidate per calling lane; an append that does not fit raises the overflow flag
+    auto emit1 = [&](float v, uint32_t doc) {
+      const int pos = atomicAdd(&s_int[2], 1);
+      if (pos < kCandCap) cand[pos] = pack_key(v, doc);
+      else *v_ovf = 1;
+    };
+    auto compact = [&]() {
+      const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
+      tau = key_score(T);
+      if (tid == 0) s_int[2] = s_int[1];
       bar_consumers();
-      int n = *v_cnt;
-      if (n > a.k) {
-        (void)block_compact_topk(cand, n, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-        n = s_int[1];
-        bar_consumers();
+    };
+    // accumulate / extract one posting (shared-space addressing)
+    auto rmw = [&](uint32_t acc0, uint32_t doc, float contrib) {
+      const uint32_t aa = acc0 + doc * 4u;
+      float old;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old) : "r"(aa));
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(__fadd_rn(old, contrib)) : "memory");
+    };
+    auto take = [&](uint32_t acc0, uint32_t doc) {
+      const uint32_t aa = acc0 + doc * 4u;
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(aa));
+      if (v != 0.f) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(0.f) : "memory");
+        if (v > tau) emit1(v, doc);
       }
-      // bitonic sort (descending) of <= 256 keys padded with 0
-      for (int i = n + tid; i < kMaxSelB; i += kConsumers) cand[i] = 0ull;
-      bar_consumers();
-      for (int size = 2; size <= kMaxSelB; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-          if (tid < kMaxSelB / 2) {
-            int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
-            int hi = lo + stride;
-            bool desc_block = ((lo & size) == 0);
-            uint64_t x = cand[lo], y = cand[hi];
-            bool swap = desc_block ? (y > x) : (x > y);
-            if (swap) { cand[lo] = y; cand[hi] = x; }
+    };
+    // One range, no prefetch state (serial redo path and term slots >= kFast): everything from global.
+    float best_v = 0.f;        // sampling mode: this lane's best (score, doc) of the range
+    uint32_t best_doc = 0;
+    auto slots_from_global = [&](int r, int g_begin, uint32_t acc0, int64_t p_lo, int64_t p_hi, int mode) {
+      const int cnt = my_term >= 0 ? (int)(p_hi - p_lo) : 0;
+      unsigned live = __ballot_sync(0xffffffffu, cnt > 0) & ~((1u << g_begin) - 1u);
+      for (unsigned rem = live; rem; rem &= rem - 1) {
+        const int g = __ffs(rem) - 1;
+        const int n = __shfl_sync(0xffffffffu, cnt, g);
+        const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p_lo, g);
+        const float w = __shfl_sync(0xffffffffu, my_w, g);
+        for (int i = lane; i < n; i += 32) {
+          const uint2 p = ldg_posting(seg + i);
+          if (mode == 0) rmw(acc0, p.x, __fmul_rn(w, __uint_as_float(p.y)));
+          else if (mode == 1) take(acc0, p.x);
+          else {  // sample: zero the slot, remember this lane's best
+            const uint32_t aa = acc0 + p.x * 4u;
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(aa));
+            if (v != 0.f) {
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(0.f) : "memory");
+              if (v > best_v) { best_v = v; best_doc = p.x; }
+            }
           }
-          bar_consumers();
+        }
+        __syncwarp();  // the same doc may recur in the next term
+      }
+      (void)r;
+    };
+
+    // ---- prologue of the per-warp pipeline: skip entries of the first range, its first chunks ----
+    int64_t p0 = 0, p1 = 0, p2 = 0;          // skip[r], skip[r + 1], skip[r + 2] of this lane's term
+    uint32_t cd[kFast], ci[kFast];           // current range: posting (lane) of fast term slot g
+    uint32_t nd[kFast], ni[kFast];           // next range
+#pragma unroll
+    for (int g = 0; g < kFast; ++g) { cd[g] = ci[g] = nd[g] = ni[g] = 0; }
+    auto load_first_chunks = [&](int64_t lo_l, int64_t hi_l, uint32_t (&d)[kFast], uint32_t (&im)[kFast]) {
+      const int cnt = my_term >= 0 ? (int)(hi_l - lo_l) : 0;
+#pragma unroll
+      for (int g = 0; g < kFast; ++g) {
+        const int n = __shfl_sync(0xffffffffu, cnt, g);
+        const long long b = __shfl_sync(0xffffffffu, (long long)lo_l, g);
+        if (lane < n) {
+          const uint2 p = ldg_posting(a.post + b + lane);
+          d[g] = p.x;
+          im[g] = p.y;
         }
       }
-      if (tid == 0) a.part_cnt[unit] = n;
-      for (int i = tid; i < n; i += kConsumers) a.part_keys[(size_t)unit * a.k + i] = cand[i];
+    };
+    if (my_n > 0 && my_term >= 0) {
+      p0 = __ldg(row + my_r0);
+      p1 = __ldg(row + my_r0 + 1);
+      p2 = my_n > 1 ? __ldg(row + my_r0 + 2) : p1;
     }
+    if (my_n > 0) load_first_chunks(p0, p1, cd, ci);
+
+    // ---- round 0: a threshold to start from.  Every warp scores its first range and contributes only
+    // each lane's best doc (<= 512 samples per CTA); the k-th best sample, one ulp lower, is a valid lower
+    // bound of the unit's k-th best score.  The samples are then dropped: the ranges are scored again
+    // below, now without the flood of appends a zero threshold would cause.
+    if (my_n > 0) {
+      const uint32_t acc0 = accw - ((uint32_t)my_r0 << a.blk_shift) * 4u;
+      slots_from_global(my_r0, 0, acc0, p0, p1, 0);
+      slots_from_global(my_r0, 0, acc0, p0, p1, 2);
+      if (best_v > 0.f) emit1(best_v, best_doc);
+    }
+    __syncthreads();
+    if (*v_cnt > a.k) {
+      const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
+      tau = f32_from_orderable((uint32_t)(T >> 32) - 1u);
+    }
+    __syncthreads();
+    if (tid == 0) s_int[2] = 0;
+    __syncthreads();
+
+    // ---- rounds ----
+    int done = 0;       // ranges of this warp's run already processed (same value in every warp)
+    int per_round = 1;
+    while (done < per_warp) {
+      const int cnt_round_start = *v_cnt;   // stable: every warp is between two round barriers
+      const int todo = min(per_round, per_warp - done);
+      for (int jj = 0; jj < todo; ++jj) {
+        const int j = done + jj;
+        if (j >= my_n) break;
+        const int r = my_r0 + j;
+        const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;  // &acc_w[doc - doc0] == acc0 + doc*4
+        // skip entry two ranges ahead, first chunks of the next range
+        int64_t p3 = p2;
+        if (my_term >= 0 && j + 3 <= my_n) p3 = __ldg(row + r + 3);
+        if (j + 1 < my_n) load_first_chunks(p1, p2, nd, ni);
+        const int cnt = my_term >= 0 ? (int)(p1 - p0) : 0;
+        const unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+        if (live) {
+          // pass 1: accumulate in term order
+#pragma unroll
+          for (int g = 0; g < kFast; ++g) {
+            if (live & (1u << g)) {
+              const int n = __shfl_sync(0xffffffffu, cnt, g);
+              const float w = __shfl_sync(0xffffffffu, my_w, g);
+              if (lane < n) rmw(acc0, cd[g], __fmul_rn(w, __uint_as_float(ci[g])));
+              if (n > 32) {
+                const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
+                for (int i = 32 + lane; i < n; i += 32) {
+                  const uint2 p = ldg_posting(seg + i);
+                  rmw(acc0, p.x, __fmul_rn(w, __uint_as_float(p.y)));
+                }
+              }
+              __syncwarp();
+            }
+          }
+          if (live >> kFast) slots_from_global(r, kFast, acc0, p0, p1, 0);
+          // pass 2: first visit of a doc takes its final score and zeroes the slot
+#pragma unroll
+          for (int g = 0; g < kFast; ++g) {
+            if (live & (1u << g)) {
+              const int n = __shfl_sync(0xffffffffu, cnt, g);
+              if (lane < n) take(acc0, cd[g]);
+              if (n > 32) {
+                const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
+                for (int i = 32 + lane; i < n; i += 32) take(acc0, ldg_posting(seg + i).x);
+              }
+              __syncwarp();
+            }
+          }
+          if (live >> kFast) slots_from_global(r, kFast, acc0, p0, p1, 1);
+        }
+        // rotate the pipeline
+        p0 = p1; p1 = p2; p2 = p3;
+#pragma unroll
+        for (int g = 0; g < kFast; ++g) { cd[g] = nd[g]; ci[g] = ni[g]; }
+      }
+
+      // ---- round barrier: overflow roll-back, compaction ----
+      __syncthreads();
+      if (*v_ovf) {
+        // Discard this round's appends, then redo its ranges one warp and one range at a time (all
+        // accumulators are zero again: pass 2 zeroes even when an append is dropped).
+        __syncthreads();
+        if (tid == 0) { s_int[2] = cnt_round_start; s_int[5] = 0; }
+        __syncthreads();
+        for (int wsel = 0; wsel < kWarps; ++wsel) {
+          for (int jj = 0; jj < todo; ++jj) {
+            const bool need = *v_cnt + kMaxBlkDocs > kCandCap;  // count is stable here; true implies count > k
+            __syncthreads();                                      // everyone has read it before anyone appends
+            if (need) compact();
+            const int j = done + jj;
+            if (warp == wsel && j < my_n) {
+              const int r = my_r0 + j;
+              const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;
+              int64_t lo_l = 0, hi_l = 0;
+              if (my_term >= 0) { lo_l = __ldg(row + r); hi_l = __ldg(row + r + 1); }
+              slots_from_global(r, 0, acc0, lo_l, hi_l, 0);
+              slots_from_global(r, 0, acc0, lo_l, hi_l, 1);
+            }
+            __syncthreads();
+          }
+        }
+        if (*v_ovf) dev_report(a.status, THR_EOVERFLOW, 440, *v_cnt);  // excluded by construction
+      }
+      // uniform after the barrier; early rounds compact sooner: a good threshold early saves appends later
+      if (*v_cnt > (per_round <= 4 ? max(2 * a.k, 256) : kCandCap / 2)) compact();
+      done += todo;
+      if (per_round < kMaxRound) per_round *= 2;
+      __syncthreads();
+    }
+
+    // ---- end of unit: final top-k, sorted ----
+    int n = *v_cnt;
+    if (n > a.k) {
+      (void)block_compact_topk(cand, n, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
+      n = s_int[1];
+      bar_consumers();
+    }
+    // bitonic sort (descending) of <= 256 keys padded with 0
+    for (int i = n + tid; i < kMaxSelB; i += kConsumers) cand[i] = 0ull;
+    bar_consumers();
+    for (int size = 2; size <= kMaxSelB; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (tid < kMaxSelB / 2) {
+          int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
+          int hi = lo + stride;
+          bool desc_block = ((lo & size) == 0);
+          uint64_t x = cand[lo], y = cand[hi];
+          bool swap = desc_block ? (y > x) : (x > y);
+          if (swap) { cand[lo] = y; cand[hi] = x; }
+        }
+        bar_consumers();
+      }
+    }
+    if (tid == 0) a.part_cnt[unit] = n;
+    for (int i = tid; i < n; i += kConsumers) a.part_keys[(size_t)unit * a.k + i] = cand[i];
   }
 }
 
@@ -530,9 +426,9 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
 // per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
-constexpr unsigned long long kRangeCost = 512;
+constexpr unsigned long long kRangeCost = 96;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
-                                                          int num_sms, Unit* units, int* unit_base,
+                                                          int num_slots, Unit* units, int* unit_base,
                                                           int* total_units, int* work_counter) {
   __shared__ unsigned long long s_tot;
   __shared__ int s_carry;
@@ -544,7 +440,7 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long lon
   for (int q = tid; q < B; q += 1024) part += (keys[q] >> 32) + kRangeCost * (unsigned long long)n_blk;
   atomicAdd(&s_tot, part);
   __syncthreads();
-  unsigned long long target = s_tot / (unsigned long long)(num_sms * 3) + 1;
+  unsigned long long target = s_tot / (unsigned long long)num_slots + 1;
   if (target < 65536ull) target = 65536ull;
   for (int q0 = 0; q0 < B; q0 += 1024) {
     const int q = q0 + tid;
@@ -676,12 +572,12 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
   THR_REQUIRE(h, n_docs >= 1 && V >= 1 && n_blk >= 1, "thr_bm25_index_set: empty index");
   int shift = 0;
   while ((1 << shift) < blk_docs) ++shift;
-  if ((1 << shift) != blk_docs || blk_docs < 1024 || blk_docs > kMaxBlkDocs)
-    return thr_fail(h, THR_EUNSUPPORTED, "thr_bm25_index_set: blk_docs = %d must be a power of two in [1024, %d]",
+  if ((1 << shift) != blk_docs || blk_docs < 256 || blk_docs > kMaxBlkDocs)
+    return thr_fail(h, THR_EUNSUPPORTED, "thr_bm25_index_set: blk_docs = %d must be a power of two in [256, %d]",
                     blk_docs, kMaxBlkDocs);
   THR_REQUIRE(h, (int64_t)n_blk * blk_docs >= n_docs && (int64_t)(n_blk - 1) * blk_docs < n_docs,
               "thr_bm25_index_set: n_blk does not match n_docs / blk_docs");
-  THR_REQUIRE(h, n_docs < ((int64_t)1 << 31), "thr_bm25_index_set: more than 2^31 docs per shard (bit 31 of a staged doc id is the owner flag)");
+  THR_REQUIRE(h, n_docs < ((int64_t)1 << 32), "thr_bm25_index_set: more than 2^32 docs per shard");
   THR_REQUIRE(h, ((uintptr_t)postings & 15u) == 0, "thr_bm25_index_set: postings must be 16-byte aligned");
   THR_REQUIRE(h, ((uintptr_t)skip & 7u) == 0, "thr_bm25_index_set: skip must be 8-byte aligned");
   thr_bm25_state_free(h);
@@ -738,7 +634,13 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
-  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, h->num_sms, units, unit_base, total_units, counter);
+  static int units_per_sm = 0;
+  if (!units_per_sm) {
+    const char* e = getenv("THR_BM25_UNITS_PER_SM");
+    units_per_sm = e ? atoi(e) : 1;  // measured: 1 beats 2..5 at 1.25M and 10M docs (fewer threshold warm-ups)
+    if (units_per_sm < 1) units_per_sm = 1;
+  }
+  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, h->num_sms * units_per_sm, units, unit_base, total_units, counter);
   THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
   bm25_order_kernel<<<32, 256, 0, s>>>(units, total_units, order);
   thr_prof_end(h, tok, s);
