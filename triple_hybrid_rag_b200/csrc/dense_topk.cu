@@ -474,21 +474,38 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
   }
   __syncthreads();
 
-  // 4. exact re-score: fp64 dot of the bf16 inputs, one warp per survivor, fixed summation order
-  for (int i = warp; i < nsel; i += kFinalThreads / 32) {
-    const uint32_t idx = key_index(sel_key[i]);
-    const __nv_bfloat16* x = a.X + (size_t)idx * a.D;
-    double acc = 0.0;
-    for (int d0 = lane * 8; d0 < a.D; d0 += 256) {
-      const uint4 xv = *reinterpret_cast<const uint4*>(x + d0);
-      const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
+  // 4. exact re-score: fp64 dot of the bf16 inputs, one warp per survivor, fixed summation order.  Four
+  //    survivors are in flight per warp so that their (cold, scattered) row reads overlap.
+  constexpr int kInFlight = 4;
+  constexpr int kWarpsF = kFinalThreads / 32;
+  for (int i0 = warp * kInFlight; i0 < nsel; i0 += kWarpsF * kInFlight) {
+    uint32_t idx[kInFlight];
+    double acc[kInFlight];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        acc = fma((double)__bfloat162float(xe[e]), (double)__bfloat162float(qrow[d0 + e]), acc);
+    for (int u = 0; u < kInFlight; ++u) {
+      idx[u] = i0 + u < nsel ? key_index(sel_key[i0 + u]) : 0u;
+      acc[u] = 0.0;
+    }
+    for (int d0 = lane * 8; d0 < a.D; d0 += 256) {
+      uint4 xv[kInFlight];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u)
+        xv[u] = *reinterpret_cast<const uint4*>(a.X + (size_t)idx[u] * a.D + d0);
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) {
+        const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          acc[u] = fma((double)__bfloat162float(xe[e]), (double)__bfloat162float(qrow[d0 + e]), acc[u]);
+      }
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) { sel_score[i] = acc; sel_idx[i] = idx; }
+    for (int u = 0; u < kInFlight; ++u) {
+      double s = acc[u];
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+      if (lane == 0 && i0 + u < nsel) { sel_score[i0 + u] = s; sel_idx[i0 + u] = idx[u]; }
+    }
   }
   for (int i = nsel + tid; i < kMaxSel; i += kFinalThreads) { sel_score[i] = -CUDART_INF; sel_idx[i] = 0xffffffffu; }
   __syncthreads();

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
   __shared__ uint16_t e_pos[kMaxEntries];
   __shared__ uint8_t e_chan[kMaxEntries];
   __shared__ uint16_t perm[kSortPad];
+  __shared__ uint16_t grp[kSortPad];   // entry indices sorted by (id, entry index)
   __shared__ uint8_t keep[kMaxEntries];
   __shared__ int s_n[4];      // entries per channel + total
   __shared__ int s_unique;
@@ -116,47 +117,76 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
   for (int i = tid; i < kSortPad; i += kFuseThreads) perm[i] = 0xffff;
   __syncthreads();
 
-  // 2. one candidate per distinct id, owned by its first occurrence
+  // 2. one candidate per distinct id, owned by its first occurrence.  Entries are sorted by (id, entry
+  //    index) with a bitonic network, so every id's occurrences form a run in entry order; the thread at
+  //    the head of a run walks it (almost always 1-3 entries) — O(n log^2 n) instead of O(n^2) scans.
   const double w[3] = {a.weights[q * 3 + 0], a.weights[q * 3 + 1], a.weights[q * 3 + 2]};
-  for (int e = tid; e < n; e += kFuseThreads) {
-    const int64_t id = e_id[e];
-    if (id < 0) continue;  // padding of a fixed-width [B,k] result (-1 past the channel's count)
-    bool first = true;
-    for (int j = 0; j < e; ++j)
-      if (e_id[j] == id) { first = false; break; }
-    if (!first) continue;
-
-    int last_rank[3] = {0, 0, 0};  // 1-based rank of the LAST occurrence per channel
-    int occ[3] = {0, 0, 0};
-    double raw[3] = {0.0, 0.0, 0.0};
-    double rrf = 0.0;
-    for (int j = e; j < n; ++j) {
-      if (e_id[j] != id) continue;
-      int c = e_chan[j];
-      int r = (int)e_pos[j] + 1;
-      last_rank[c] = r;
-      occ[c] += 1;
-      if (kVariant == THR_FUSE_LIB) raw[c] = e_raw[c][j];                  // last one wins
-      if (kVariant == THR_FUSE_RAG1) {
-        raw[c] = fmax(raw[c], e_raw[c][j]);                                // best individual score
-        rrf = __dadd_rn(rrf, __ddiv_rn(1.0, (double)(a.rrf_k + r)));       // r = rank0 + 1
+  {
+    int P2 = 32;
+    while (P2 < n) P2 <<= 1;
+    for (int i = tid; i < P2; i += kFuseThreads) grp[i] = i < n ? (uint16_t)i : 0xffff;
+    __syncthreads();
+    auto id_before = [&](uint16_t x, uint16_t y) -> bool {  // x strictly before y; padding (id < 0) last
+      if (x == 0xffff) return false;
+      if (y == 0xffff) return true;
+      const int64_t ix = e_id[x], iy = e_id[y];
+      const bool px = ix < 0, py = iy < 0;
+      if (px != py) return py;
+      if (ix != iy) return ix < iy;
+      return x < y;
+    };
+    for (int size = 2; size <= P2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < (P2 >> 1); i += kFuseThreads) {
+          int lo = ((i / stride) * (stride << 1)) + (i % stride);
+          int hi = lo + stride;
+          bool ascending = ((lo & size) == 0);
+          uint16_t x = grp[lo], y = grp[hi];
+          bool swap = ascending ? id_before(y, x) : id_before(x, y);
+          if (swap) { grp[lo] = y; grp[hi] = x; }
+        }
+        __syncthreads();
       }
     }
+  }
+  for (int i = tid; i < n; i += kFuseThreads) {
+    const int e = grp[i];
+    const int64_t id = e_id[e];
+    if (id < 0) continue;  // padding of a fixed-width [B,k] result (-1 past the channel's count)
+    if (i > 0 && e_id[grp[i - 1]] == id) continue;  // not the head of its run
+
+    int rank0 = 0, rank1 = 0, rank2 = 0;  // 1-based rank of the LAST occurrence per channel
+    int occ0 = 0, occ1 = 0, occ2 = 0;
+    double raw0 = 0.0, raw1 = 0.0, raw2 = 0.0;
+    double rrf = 0.0;
+    for (int t = i; t < n; ++t) {
+      const int j = grp[t];
+      if (e_id[j] != id) break;
+      const int c = e_chan[j];
+      const int r = (int)e_pos[j] + 1;
+      const double rv = e_raw[c][j];
+      if (c == 0) { rank0 = r; occ0 += 1; raw0 = kVariant == THR_FUSE_RAG1 ? fmax(raw0, rv) : rv; }
+      else if (c == 1) { rank1 = r; occ1 += 1; raw1 = kVariant == THR_FUSE_RAG1 ? fmax(raw1, rv) : rv; }
+      else { rank2 = r; occ2 += 1; raw2 = kVariant == THR_FUSE_RAG1 ? fmax(raw2, rv) : rv; }
+      if (kVariant == THR_FUSE_RAG1) rrf = __dadd_rn(rrf, __ddiv_rn(1.0, (double)(a.rrf_k + r)));  // r = rank0 + 1
+    }
+    const int last_rank[3] = {rank0, rank1, rank2};
+    const int occ[3] = {occ0, occ1, occ2};
     if (kVariant == THR_FUSE_RAG2) {
+#pragma unroll
       for (int c = 0; c < 3; ++c)
         if (last_rank[c]) rrf = __dadd_rn(rrf, __ddiv_rn(w[c], (double)(a.rrf_k + last_rank[c])));
     } else if (kVariant == THR_FUSE_LIB) {
+#pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (!occ[c]) continue;
-        double s = __dmul_rn(w[c], __ddiv_rn(1.0, (double)(a.rrf_k + last_rank[c])));
-        for (int k = 0; k < occ[c]; ++k) rrf = __dadd_rn(rrf, s);  // the merge loop adds once per occurrence
+        double sc = __dmul_rn(w[c], __ddiv_rn(1.0, (double)(a.rrf_k + last_rank[c])));
+        for (int k = 0; k < occ[c]; ++k) rrf = __dadd_rn(rrf, sc);  // the merge loop adds once per occurrence
       }
     }
     e_rrf[e] = rrf;
-    for (int c = 0; c < 3; ++c) {
-      e_rank[c][e] = (uint16_t)last_rank[c];
-      e_raw[c][e] = raw[c];
-    }
+    e_rank[0][e] = (uint16_t)rank0; e_rank[1][e] = (uint16_t)rank1; e_rank[2][e] = (uint16_t)rank2;
+    e_raw[0][e] = raw0; e_raw[1][e] = raw1; e_raw[2][e] = raw2;
     int slot = atomicAdd(&s_unique, 1);
     perm[slot] = (uint16_t)e;
   }
