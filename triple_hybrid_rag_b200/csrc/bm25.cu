@@ -17,9 +17,10 @@
 // per posting.  Therefore every warp is autonomous: it OWNS whole ranges — a contiguous run of the unit's
 // ranges, with a private 2048-slot fp32 accumulator in shared memory — and does everything for them:
 //   * reads the terms' skip entries (lane t <-> query term t, loaded two ranges ahead),
-//   * loads the terms' posting segments straight from global memory, coalesced; the first 32 postings of
-//     each of the first 8 terms are prefetched into registers one range ahead, so DRAM latency overlaps the
-//     previous range's arithmetic,
+//   * pulls the terms' posting segments of the NEXT range into its own double-buffered staging area in
+//     shared memory with cp.async.bulk (one copy per term, issued by the term's lane, completion on a
+//     per-warp mbarrier) and hints the range after that into L2, so DRAM latency overlaps the current
+//     range's arithmetic (segments that do not fit the 272-posting buffer are read from global),
 //   * accumulates term by term in query order (__syncwarp between terms: no atomics, no block barriers),
 //   * re-walks the postings, takes each touched doc's final score once, re-zeroes the slot and appends the
 //     score to the CTA's candidate list if it beats the running threshold tau.
@@ -39,8 +40,8 @@ constexpr int kThreads = kWarps * 32;            // 512
 constexpr int kConsumers = kThreads;
 constexpr int kMaxBlkDocs = 2048;                // docs per range = accumulator slots per warp
 constexpr int kMaxSelB = 256;
-constexpr int kCandCap = 4608;                   // >= kMaxBlkDocs + 2 * kMaxSelB
-constexpr int kFast = 8;                         // term slots with register-prefetched first chunks
+constexpr int kCandCap = 2560;                   // >= kMaxBlkDocs + 2 * kMaxSelB
+constexpr int kStage = 272;                      // postings per warp staging buffer (two per warp)
 constexpr int kMaxRound = 8;                     // ranges per warp and round, at most
 
 struct Posting { uint32_t doc; float imp; };
@@ -73,6 +74,11 @@ __device__ __forceinline__ uint2 ldg_posting(const Posting* p) {
   uint2 v;
   asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
+}
+
+// Pull [p, p + bytes) into L2 (16-byte granules); no destination, no completion to wait for.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // Block-cooperative: keep the ksel largest of keys[0..n) in place, n > ksel.
@@ -122,8 +128,10 @@ __device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t
 
 constexpr size_t kSmemAcc = (size_t)kWarps * kMaxBlkDocs * 4;
 constexpr size_t kSmemCand = (size_t)kCandCap * 8;
-constexpr size_t kSmemMisc = 256 * 4 + kMaxTerms * 8 + 8 + 8 * 4;
-constexpr size_t kBm25Smem = kSmemAcc + kSmemCand + kSmemMisc + 256;
+constexpr size_t kSmemStage = (size_t)kWarps * 2 * kStage * sizeof(Posting);
+constexpr size_t kSmemMisc = 256 * 4 + kMaxTerms * 8 + 8 + 8 * 4 + kWarps * 2 * 8;
+constexpr size_t kBm25Smem = kSmemAcc + kSmemCand + kSmemStage + kSmemMisc + 256;
+static_assert(kBm25Smem <= 232448, "shared memory budget of one SM");
 
 __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -131,7 +139,9 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* acc = (float*)gen;                                                    // [kWarps][kMaxBlkDocs]
   uint64_t* cand = (uint64_t*)(acc + kWarps * kMaxBlkDocs);                    // kCandCap
-  uint32_t* hist = (uint32_t*)(cand + kCandCap);                              // 256
+  Posting* stage = (Posting*)(cand + kCandCap);                               // [kWarps][2][kStage]
+  uint64_t* sbar = (uint64_t*)(stage + kWarps * 2 * kStage);                  // [kWarps][2] mbarriers
+  uint32_t* hist = (uint32_t*)(sbar + kWarps * 2);                            // 256
   int* q_term = (int*)(hist + 256);                                           // kMaxTerms
   float* q_idf = (float*)(q_term + kMaxTerms);                                // kMaxTerms
   unsigned long long* s_prefix = (unsigned long long*)(q_idf + kMaxTerms);
@@ -139,6 +149,15 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < kWarps * kMaxBlkDocs; i += kThreads) acc[i] = 0.f;
+  if (lane == 0) {
+    mbar_init(smem_u32(&sbar[warp * 2]), 1);
+    mbar_init(smem_u32(&sbar[warp * 2 + 1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t stage_w = smem_u32(stage + (size_t)warp * 2 * kStage);       // this warp's two staging buffers
+  const uint32_t sbar_w = smem_u32(&sbar[warp * 2]);
+  uint32_t seq = 0;   // staged ranges so far (per warp, across units): buffer = seq & 1, parity = (seq >> 1) & 1
   const uint32_t accw = smem_u32(acc) + (uint32_t)warp * kMaxBlkDocs * 4u;   // this warp's accumulator
   volatile int* v_cnt = &s_int[2];
   volatile int* v_ovf = &s_int[5];
@@ -240,31 +259,51 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       (void)r;
     };
 
-    // ---- prologue of the per-warp pipeline: skip entries of the first range, its first chunks ----
+    // ---- prologue of the per-warp pipeline: skip entries of the first ranges ----
     int64_t p0 = 0, p1 = 0, p2 = 0;          // skip[r], skip[r + 1], skip[r + 2] of this lane's term
-    uint32_t cd[kFast], ci[kFast];           // current range: posting (lane) of fast term slot g
-    uint32_t nd[kFast], ni[kFast];           // next range
-#pragma unroll
-    for (int g = 0; g < kFast; ++g) { cd[g] = ci[g] = nd[g] = ni[g] = 0; }
-    auto load_first_chunks = [&](int64_t lo_l, int64_t hi_l, uint32_t (&d)[kFast], uint32_t (&im)[kFast]) {
-      const int cnt = my_term >= 0 ? (int)(hi_l - lo_l) : 0;
-#pragma unroll
-      for (int g = 0; g < kFast; ++g) {
-        const int n = __shfl_sync(0xffffffffu, cnt, g);
-        const long long b = __shfl_sync(0xffffffffu, (long long)lo_l, g);
-        if (lane < n) {
-          const uint2 p = ldg_posting(a.post + b + lane);
-          d[g] = p.x;
-          im[g] = p.y;
-        }
-      }
-    };
     if (my_n > 0 && my_term >= 0) {
       p0 = __ldg(row + my_r0);
       p1 = __ldg(row + my_r0 + 1);
       p2 = my_n > 1 ? __ldg(row + my_r0 + 2) : p1;
     }
-    if (my_n > 0) load_first_chunks(p0, p1, cd, ci);
+    // Stage the postings [lo_l, hi_l) of every term (lane) into buffer (seq_no & 1).  Returns this lane's
+    // offset of its first posting inside the buffer, or -1 when its segment did not fit (read from global).
+    auto stage_issue = [&](int64_t lo_l, int64_t hi_l, uint32_t seq_no) -> int {
+      const int cnt = my_term >= 0 ? (int)(hi_l - lo_l) : 0;
+      const int slack = (int)(lo_l & 1);                       // copies start at an even posting (16-byte granules)
+      const int cp = cnt > 0 ? ((slack + cnt + 1) & ~1) : 0;   // postings copied
+      int incl = cp;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const bool fits = cnt > 0 && incl <= kStage;             // a prefix of the terms (in order) is staged
+      const unsigned staged = __ballot_sync(0xffffffffu, fits);
+      int bytes = fits ? cp * 8 : 0;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, sft);
+      const uint32_t bar = sbar_w + (seq_no & 1u) * 8u;
+      fence_proxy_async_smem();   // this warp's earlier reads of the buffer precede the async writes
+      if (lane == 0) {
+        if (bytes > 0) mbar_arrive_expect_tx(bar, (uint32_t)bytes);
+        else mbar_arrive(bar);
+      }
+      __syncwarp();
+      const int off = incl - cp;
+      if (fits) {
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            :
+            : "r"(stage_w + ((seq_no & 1u) * kStage + (uint32_t)off) * 8u), "l"(a.post + (lo_l - slack)),
+              "r"((uint32_t)cp * 8u), "r"(bar)
+            : "memory");
+      }
+      (void)staged;
+      return fits ? off + slack : -1;
+    };
+    int cur_off = -1, nxt_off = -1;
+    if (my_n > 0) cur_off = stage_issue(p0, p1, seq);
 
     // ---- round 0: a threshold to start from.  Every warp scores its first range and contributes only
     // each lane's best doc (<= 512 samples per CTA); the k-th best sample, one ulp lower, is a valid lower
@@ -296,50 +335,80 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
         if (j >= my_n) break;
         const int r = my_r0 + j;
         const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;  // &acc_w[doc - doc0] == acc0 + doc*4
-        // skip entry two ranges ahead, first chunks of the next range
+        // skip entry three ranges ahead (used at the end of this range), next range's postings -> staging
         int64_t p3 = p2;
         if (my_term >= 0 && j + 3 <= my_n) p3 = __ldg(row + r + 3);
-        if (j + 1 < my_n) load_first_chunks(p1, p2, nd, ni);
+        if (j + 1 < my_n) nxt_off = stage_issue(p1, p2, seq + 1);
         const int cnt = my_term >= 0 ? (int)(p1 - p0) : 0;
         const unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+        // this range's staged postings have landed?
+        mbar_wait(sbar_w + (seq & 1u) * 8u, (seq >> 1) & 1u, a.status, 450);
+        const uint32_t sbuf = stage_w + (seq & 1u) * kStage * 8u;
+        ++seq;
         if (live) {
           // pass 1: accumulate in term order
-#pragma unroll
-          for (int g = 0; g < kFast; ++g) {
-            if (live & (1u << g)) {
-              const int n = __shfl_sync(0xffffffffu, cnt, g);
-              const float w = __shfl_sync(0xffffffffu, my_w, g);
-              if (lane < n) rmw(acc0, cd[g], __fmul_rn(w, __uint_as_float(ci[g])));
-              if (n > 32) {
-                const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
-                for (int i = 32 + lane; i < n; i += 32) {
-                  const uint2 p = ldg_posting(seg + i);
-                  rmw(acc0, p.x, __fmul_rn(w, __uint_as_float(p.y)));
-                }
+          for (unsigned rem = live; rem; rem &= rem - 1) {
+            const int g = __ffs(rem) - 1;
+            const int n = __shfl_sync(0xffffffffu, cnt, g);
+            const int off = __shfl_sync(0xffffffffu, cur_off, g);
+            const float w = __shfl_sync(0xffffffffu, my_w, g);
+            if (off >= 0) {
+              const uint32_t end = sbuf + (uint32_t)(off + n) * 8u;
+              for (uint32_t pa = sbuf + (uint32_t)(off + lane) * 8u; pa < end; pa += 256u) {
+                uint32_t doc;
+                float imp;
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(doc), "=f"(imp) : "r"(pa));
+                rmw(acc0, doc, __fmul_rn(w, imp));
               }
-              __syncwarp();
+            } else {  // did not fit the staging buffer: four chunks in flight from global
+              const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
+              for (int i = lane; i < n; i += 128) {
+                uint2 pp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (i + 32 * u < n) pp[u] = ldg_posting(seg + i + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (i + 32 * u < n) rmw(acc0, pp[u].x, __fmul_rn(w, __uint_as_float(pp[u].y)));
+              }
             }
+            __syncwarp();  // the same doc may recur in the next term
           }
-          if (live >> kFast) slots_from_global(r, kFast, acc0, p0, p1, 0);
           // pass 2: first visit of a doc takes its final score and zeroes the slot
-#pragma unroll
-          for (int g = 0; g < kFast; ++g) {
-            if (live & (1u << g)) {
-              const int n = __shfl_sync(0xffffffffu, cnt, g);
-              if (lane < n) take(acc0, cd[g]);
-              if (n > 32) {
-                const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
-                for (int i = 32 + lane; i < n; i += 32) take(acc0, ldg_posting(seg + i).x);
+          for (unsigned rem = live; rem; rem &= rem - 1) {
+            const int g = __ffs(rem) - 1;
+            const int n = __shfl_sync(0xffffffffu, cnt, g);
+            const int off = __shfl_sync(0xffffffffu, cur_off, g);
+            if (off >= 0) {
+              const uint32_t end = sbuf + (uint32_t)(off + n) * 8u;
+              for (uint32_t pa = sbuf + (uint32_t)(off + lane) * 8u; pa < end; pa += 256u) {
+                uint32_t doc;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(doc) : "r"(pa));
+                take(acc0, doc);
               }
-              __syncwarp();
+            } else {
+              const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
+              for (int i = lane; i < n; i += 128) {
+                uint32_t dd[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (i + 32 * u < n) dd[u] = ldg_posting(seg + i + 32 * u).x;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (i + 32 * u < n) take(acc0, dd[u]);
+              }
             }
+            __syncwarp();
           }
-          if (live >> kFast) slots_from_global(r, kFast, acc0, p0, p1, 1);
+        }
+        // this term's postings three ranges ahead -> L2 (the staging copy then hits L2, not DRAM)
+        if (p3 > p2) {
+          const int64_t b = p2 & ~(int64_t)1;
+          prefetch_l2_bulk(a.post + b, (uint32_t)(((p3 - b) * 8 + 15) & ~(int64_t)15));
         }
         // rotate the pipeline
         p0 = p1; p1 = p2; p2 = p3;
-#pragma unroll
-        for (int g = 0; g < kFast; ++g) { cd[g] = nd[g]; ci[g] = ni[g]; }
+        cur_off = nxt_off;
       }
 
       // ---- round barrier: overflow roll-back, compaction ----
