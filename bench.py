@@ -32,7 +32,7 @@ GEN_DOCS = 262144
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=int(os.environ.get("THR_BENCH_CHUNKS", 10_000_000)))
@@ -322,6 +322,14 @@ def main():
         return
 
     burst, sustained, hbm, which = peaks()
+    traffic = {}
+    try:  # DRAM bytes per launch from the committed ncu capture of this exact configuration, else null
+        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        c = tj["config"]
+        if (c["chunks"], c["dim"], c["batch"], c["n_gpus"]) == (N, D, B, world):
+            traffic = tj
+    except Exception:
+        pass
     dense_ms, dense_n = prof.get("dense_score", (0.0, 0))
     dense_avg = dense_ms / max(dense_n, 1)
     flops = 2.0 * B * (hi - lo) * D
@@ -341,7 +349,9 @@ def main():
         "latency": {"p50_ms_batch256_e2e": statistics.median(lat) * 1e3, "p50_ms_batch1_e2e": statistics.median(lat1) * 1e3},
         "stages_ms": stages,
         "roofline": {"kernel": "dense_score_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained,
-                     "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None,
+                     "traffic": traffic.get("dense_score_kernel", {}).get("dram_bytes_per_launch"),
+                     "algorithmic_bytes": x_bytes + 2.0 * B * D,
                      "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
                      "frac_of_burst": achieved / burst if burst else None,
                      "hbm_gbs": x_bytes / (dense_avg * 1e-3) / 1e9 if dense_avg > 0 else 0.0,
@@ -349,7 +359,8 @@ def main():
                      "launch_ms": dense_avg, "launches": dense_n},
         "bm25_roofline": {"kernel": "bm25_kernel", "bound": "hbm", "algorithmic_bytes": bm25_bytes,
                           "achieved": bm25_bytes / (bm25_ms * 1e-3) / 1e9 if bm25_ms > 0 else 0.0, "peak": hbm,
-                          "unit": "GB/s", "frac": (bm25_bytes / (bm25_ms * 1e-3) / 1e9) / hbm if bm25_ms > 0 else None},
+                          "unit": "GB/s", "frac": (bm25_bytes / (bm25_ms * 1e-3) / 1e9) / hbm if bm25_ms > 0 else None,
+                          "traffic": traffic.get("bm25_kernel", {}).get("dram_bytes_per_launch")},
         "setup_s": round(setup_s, 1),
     }
     if world == 1 and not args.no_cpu_baseline:
