@@ -55,3 +55,25 @@ def test_bm25_fp32_within_tolerance_of_fp64(engine):
     for q, s, c in zip(qs, s32, cnt):
         ref = np.sort(ob.bm25_scores_fp64(orc, q))[::-1][:c]
         assert np.allclose(np.sort(s[:c])[::-1], ref, rtol=1e-3)
+
+
+def test_bm25_exact_score_ties_resolve_by_doc_id(engine):
+    """Thousands of docs with identical (tf, length) for the query terms score EXACTLY the same; the k
+    best must be the smallest ids even though the kernel's warps walk different doc runs concurrently
+    (a tying doc with a smaller id can arrive after the threshold was raised to that very score)."""
+    n_docs, V = 60_000, 64
+    rng = np.random.default_rng(11)
+    doc_l, term_l, tf_l = [], [], []
+    L = np.full(n_docs, 50, dtype=np.int64)
+    for t, (step, tfv) in enumerate([(1, 2), (3, 1), (7, 3), (2, 2)]):      # regular patterns -> massive ties
+        d = np.arange(t, n_docs, step)
+        doc_l.append(d); term_l.append(np.full(d.size, t)); tf_l.append(np.full(d.size, tfv))
+    d = np.sort(rng.choice(n_docs, 500, replace=False))                       # a rare term breaks some ties
+    doc_l.append(d); term_l.append(np.full(d.size, 9)); tf_l.append(rng.integers(1, 4, d.size))
+    doc, term, tf = (torch.from_numpy(np.concatenate(x)) for x in (doc_l, term_l, tf_l))
+    Lt = torch.from_numpy(L)
+    idx = BM25Index.build(doc, term, tf.to(torch.int32), Lt, V, blk_docs=2048)
+    orc = ob.CsrIndex.from_coo(doc.numpy(), term.numpy(), tf.numpy(), L, V)
+    qs = [[0], [1], [2, 3], [0, 1, 2, 3], [9, 0], [3, 9, 1]] * 3
+    for k in (1, 10, 100, 256):
+        _check(engine, idx, orc, qs, k)

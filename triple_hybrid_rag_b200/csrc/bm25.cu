@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
     };
     auto compact = [&]() {
       const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-      tau = key_score(T);
+      // One ulp below the k-th best score: warps walk their runs concurrently, so a doc that TIES with the
+      // k-th best can still arrive later with a smaller id and must pass the strict "> tau" filter.
+      tau = f32_from_orderable((uint32_t)(T >> 32) - 1u);
       if (tid == 0) s_int[2] = s_int[1];
       bar_consumers();
     };
