@@ -40,24 +40,31 @@ def exchange_topk(group, world, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc
     """The one exchange step of the sharded path: every rank contributes its local top-k lists of both
     channels (ids already global: the kernels add the shard's id_base), one all-gather per array, then
     merge_fn (K5 on the GPU) reduces G x k -> k per query on every rank, so the fusion runs replicated.
+    The three arrays travel in one byte message: one collective per step (it is latency-bound).
     merge_fn(scores [G,2B,k] f64, ids [G,2B,k] i64, counts [G,2B] i32, k) -> (scores, ids, counts)."""
     import torch.distributed as dist
     dev, G = d_ids.device, world
     k = max(k_sem, k_lex)
-    sc = torch.full((2, B, k), float("-inf"), dtype=torch.float64, device=dev)
-    ids = torch.full((2, B, k), -1, dtype=torch.int64, device=dev)
+    # one message per rank: [scores f64 | ids i64 | counts i32] packed into a byte buffer -> ONE all-gather
+    n_sc = 2 * B * k * 8
+    n_cnt = 2 * B * 4
+    msg = torch.empty((2 * n_sc + n_cnt,), dtype=torch.uint8, device=dev)
+    sc = msg[:n_sc].view(torch.float64).view(2, B, k)
+    ids = msg[n_sc:2 * n_sc].view(torch.int64).view(2, B, k)
+    cnt = msg[2 * n_sc:].view(torch.int32).view(2, B)
+    sc.fill_(float("-inf"))
+    ids.fill_(-1)
     sc[0, :, :k_sem] = d_sc
     sc[1, :, :k_lex] = l_sc.to(torch.float64)
     ids[0, :, :k_sem] = d_ids
     ids[1, :, :k_lex] = l_ids
-    cnt = torch.stack([d_cnt, l_cnt]).contiguous()
-    g_sc = torch.empty((G, 2 * B, k), dtype=torch.float64, device=dev)
-    g_ids = torch.empty((G, 2 * B, k), dtype=torch.int64, device=dev)
-    g_cnt = torch.empty((G, 2 * B), dtype=torch.int32, device=dev)
-    # flat [G*2B, ...] output views: accepted by NCCL and by gloo (the CPU tests)
-    dist.all_gather_into_tensor(g_sc.view(G * 2 * B, k), sc.view(2 * B, k), group=group)
-    dist.all_gather_into_tensor(g_ids.view(G * 2 * B, k), ids.view(2 * B, k), group=group)
-    dist.all_gather_into_tensor(g_cnt.view(G * 2 * B), cnt.view(2 * B), group=group)
+    cnt[0] = d_cnt
+    cnt[1] = l_cnt
+    gathered = torch.empty((G, msg.numel()), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1), msg, group=group)
+    g_sc = gathered[:, :n_sc].contiguous().view(torch.float64).view(G, 2 * B, k)
+    g_ids = gathered[:, n_sc:2 * n_sc].contiguous().view(torch.int64).view(G, 2 * B, k)
+    g_cnt = gathered[:, 2 * n_sc:].contiguous().view(torch.int32).view(G, 2 * B)
     m_sc, m_ids, m_cnt = merge_fn(g_sc, g_ids, g_cnt, k)  # dense rows then lexical rows
     l_ids = m_ids[B:, :k_lex].contiguous()
     l_sc = m_sc[B:, :k_lex].to(torch.float32)
