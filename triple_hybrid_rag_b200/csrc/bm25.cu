@@ -497,9 +497,10 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
 // per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
-constexpr unsigned long long kRangeCost = 96;
+constexpr unsigned long long kRangeCostDefault = 96;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
-                                                          int num_slots, Unit* units, int* unit_base,
+                                                          int num_slots, unsigned long long kRangeCost,
+                                                          Unit* units, int* unit_base,
                                                           int* total_units, int* work_counter) {
   __shared__ unsigned long long s_tot;
   __shared__ int s_carry;
@@ -711,7 +712,13 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
     units_per_sm = e ? atoi(e) : 1;  // measured: 1 beats 2..5 at 1.25M and 10M docs (fewer threshold warm-ups)
     if (units_per_sm < 1) units_per_sm = 1;
   }
-  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, h->num_sms * units_per_sm, units, unit_base, total_units, counter);
+  static long long range_cost = -1;
+  if (range_cost < 0) {
+    const char* e = getenv("THR_BM25_RANGE_COST");
+    range_cost = e ? atoll(e) : (long long)kRangeCostDefault;
+  }
+  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, h->num_sms * units_per_sm, (unsigned long long)range_cost, units,
+                                      unit_base, total_units, counter);
   THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
   bm25_order_kernel<<<32, 256, 0, s>>>(units, total_units, order);
   thr_prof_end(h, tok, s);

@@ -10,7 +10,9 @@
 // 128 rows, rows >= q_len are ignored by the epilogue) stays in shared memory, candidates stream
 // through a TMA ring (one candidate = Td x 128 bf16 = one stage), one tcgen05.mma chain of 8 K-steps
 // per candidate into one of 4 TMEM accumulators (128 lanes x Td columns), and the epilogue does the
-// row max (over TMEM columns, in registers) and the sum over query tokens (warp shuffle + 4 partials).
+// row max (over TMEM columns, in registers) and the sum over query tokens.  For Tq <= 32 (<= 64) the
+// query tile is stacked 4 (2) times in the 128 MMA rows: every epilogue warp then owns valid TMEM lanes and
+// scans only a quarter (half) of the doc-token columns; partial maxima meet in shared memory.
 // The scores matrix [Tq x Td] never leaves the SM.  At Tq = 32 the kernel is HBM-bound
 // (2*Tq = 64 FLOP per byte of candidate tokens).
 #include <math_constants.h>
@@ -36,6 +38,7 @@ struct MaxSimArgs {
   float* out;
   int slices;       // candidate slices per query
   int per_slice;    // candidates per slice
+  int reps;         // copies of the query tile stacked in the 128 MMA rows (4 for Tq <= 32, 2 for Tq <= 64, else 1)
   thr_dev_status* status;
 };
 
@@ -56,7 +59,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const uint32_t qfull_bar = bar_base + 8u * (2 * kStagesM + 2 * kAccM);
   const uint32_t qempty_bar = qfull_bar + 8u;
   const uint32_t tmem_slot = qempty_bar + 8u;
-  __shared__ float part[kAccM][4];
+  __shared__ float pmax[kAccM][128];   // [accumulator][replica * rows_per_rep + token]: partial row maxima
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -87,8 +90,13 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         // query tile: wait until the MMAs of the previous unit no longer read it
         mbar_wait(qempty_bar, (ucount & 1u) ^ 1u, a.status, 500);
         mbar_arrive_expect_tx(qfull_bar, kATileBytes);
-        tma_load_2d(a_smem, &map_q, qfull_bar, 0, b * a.Tq, THR_L2_EVICT_LAST);
-        tma_load_2d(a_smem + 128 * 64 * 2, &map_q, qfull_bar, 64, b * a.Tq, THR_L2_EVICT_LAST);
+        // the query tile is stacked `reps` times in the 128 rows so that every epilogue warp owns valid rows
+        const int rows_per_rep = 128 / a.reps;
+        for (int rp = 0; rp < a.reps; ++rp) {
+          const uint32_t dst = a_smem + (uint32_t)(rp * rows_per_rep) * 128u;
+          tma_load_2d(dst, &map_q, qfull_bar, 0, b * a.Tq, THR_L2_EVICT_LAST);
+          tma_load_2d(dst + 128 * 64 * 2, &map_q, qfull_bar, 64, b * a.Tq, THR_L2_EVICT_LAST);
+        }
         for (int c = c_lo; c < c_hi; ++c, ++it) {
           const int s = it % kStagesM;
           const uint32_t ph = (it / kStagesM) & 1u;
@@ -136,15 +144,20 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else {
     // ===================== epilogue: row max over doc tokens, sum over query tokens =====================
+    // TMEM lane quarter w belongs to warp w.  With the query tile stacked `reps` times, replica r (rows
+    // r*rows_per_rep ..) only scans doc-token columns [r*Td/reps, (r+1)*Td/reps): the four warps split the
+    // columns instead of three of them idling; partial maxima meet in shared memory, warp 0 sums.
     const uint32_t lane_base = warp * 32;
-    const int row = (int)(lane_base + lane);  // query token index
+    const int rows_per_rep = 128 / a.reps;
+    const int my_row = (int)(lane_base + lane);
+    const int rep = my_row / rows_per_rep;
+    const int cols_per_rep = a.Td / a.reps;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int b = u / a.slices, sl = u % a.slices;
       const int c_lo = sl * a.per_slice, c_hi = min(a.C, c_lo + a.per_slice);
       int ql = a.q_len ? a.q_len[b] : a.Tq;
       ql = max(0, min(ql, a.Tq));
-      const bool warp_active = (int)lane_base < ql;
       for (int c = c_lo; c < c_hi; ++c, ++it) {
         const int acc = it % kAccM;
         const uint32_t aph = (it / kAccM) & 1u;
@@ -155,26 +168,33 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_wait(tfull_bar(acc), aph, a.status, 520);
         tc_fence_after_sync();
         float m = -CUDART_INF_F;
-        if (warp_active && doc_ok) {
-          for (int c0 = 0; c0 < dl; c0 += 32) {
+        const int col_lo = rep * cols_per_rep, col_hi = min(dl, col_lo + cols_per_rep);
+        if (doc_ok && (int)(lane_base % rows_per_rep) < ql) {   // warp-uniform: some row of this warp is a live token
+          for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + (lane_base << 16) + (uint32_t)(acc * 128 + c0), r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c0 + j < dl) m = fmaxf(m, __uint_as_float(r[j]));
+              if (c0 + j < col_hi) m = fmaxf(m, __uint_as_float(r[j]));
           }
         }
-        float v = (row < ql && dl > 0 && doc_ok) ? m : 0.f;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        if (lane == 0) part[acc][warp] = v;
+        pmax[acc][my_row] = m;
         tc_fence_before_sync();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 0) {
-          float s = ((part[acc][0] + part[acc][1]) + part[acc][2]) + part[acc][3];
-          a.out[(size_t)b * a.C + c] = doc_ok ? s : -CUDART_INF_F;
-          mbar_arrive(tempty_bar(acc));  // every epilogue warp has passed the barrier above
+        if (warp == 0) {
+          float v = 0.f;
+          for (int t = (int)lane; t < rows_per_rep; t += 32) {
+            float mm = pmax[acc][t];
+            for (int rp = 1; rp < a.reps; ++rp) mm = fmaxf(mm, pmax[acc][rp * rows_per_rep + t]);
+            if (t < ql && dl > 0 && doc_ok) v += mm;
+          }
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+          if (lane == 0) {
+            a.out[(size_t)b * a.C + c] = doc_ok ? v : -CUDART_INF_F;
+            mbar_arrive(tempty_bar(acc));  // every epilogue warp has passed the barrier above
+          }
         }
       }
     }
@@ -205,13 +225,15 @@ int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int
   if (Tq < 1 || Tq > 128) return thr_fail(h, THR_EUNSUPPORTED, "thr_maxsim: Tq = %d must be in [1, 128]", Tq);
   THR_REQUIRE(h, n_docs >= 1 && n_docs * Td < ((int64_t)1 << 31), "thr_maxsim: token store too large for TMA row index");
   CUtensorMap map_q, map_d;
-  int rc = thr_encode_tma_2d_bf16(h, &map_q, Qtok, (uint64_t)B * Tq, kD, 128, 64);
+  const uint32_t q_box_rows = Tq <= 32 ? 32u : (Tq <= 64 ? 64u : 128u);   // one replica of the query tile per load
+  int rc = thr_encode_tma_2d_bf16(h, &map_q, Qtok, (uint64_t)B * Tq, kD, q_box_rows, 64);
   if (rc != THR_OK) return rc;
   rc = thr_encode_tma_2d_bf16(h, &map_d, Dtok, (uint64_t)n_docs * Td, kD, (uint32_t)Td, 64);
   if (rc != THR_OK) return rc;
   MaxSimArgs a;
   a.B = B; a.Tq = Tq; a.Td = Td; a.C = C; a.n_docs = n_docs; a.q_len = q_len; a.d_len = d_len;
   a.cand = cand; a.out = out; a.status = h->d_status;
+  a.reps = Tq <= 32 ? 4 : (Tq <= 64 ? 2 : 1);
   int slices = (4 * h->num_sms + B - 1) / B;
   if (slices < 1) slices = 1;
   if (slices > C) slices = C;
