@@ -77,3 +77,15 @@ def test_bm25_exact_score_ties_resolve_by_doc_id(engine):
     qs = [[0], [1], [2, 3], [0, 1, 2, 3], [9, 0], [3, 9, 1]] * 3
     for k in (1, 10, 100, 256):
         _check(engine, idx, orc, qs, k)
+
+
+def test_bm25_too_many_terms_is_an_error(engine):
+    from triple_hybrid_rag_b200._lib import ThrError
+    idx, _ = _corpus(3_000, 500, 256)
+    d = idx.to(engine.device)
+    engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V)
+    qt, qo = pack_queries([list(range(33)), [1, 2]], engine.device)
+    engine.bm25_topk(qt, qo, 10)
+    with pytest.raises(ThrError, match="32 terms"):
+        engine.sync()
+    engine.sync()  # the status word is cleared: the handle stays usable

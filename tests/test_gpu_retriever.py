@@ -247,6 +247,19 @@ def test_retrieve_batch_matches_oracle_fusion(engine):
         assert got == [(x["id"], x["rrf"].hex(), x["ranks"]) for x in rows]
 
 
+def test_resident_index_save_load(engine, tmp_path):
+    chunks, emb, parents = _corpus(300, 64, seed=8)
+    ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=256)
+    r = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"q": emb[5].tolist()}), index=ix)
+    want_l = asyncio.run(r._lexical_search(["w2", "w11"], None, 20))
+    want_s = asyncio.run(r._semantic_search("q", None, 20))
+    ix.save(tmp_path / "ix.pt")
+    ix2 = ResidentIndex.load(engine, tmp_path / "ix.pt")
+    r2 = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"q": emb[5].tolist()}), index=ix2)
+    assert asyncio.run(r2._lexical_search(["w2", "w11"], None, 20)) == want_l
+    assert asyncio.run(r2._semantic_search("q", None, 20)) == want_s
+
+
 def test_no_engine_fails_loudly():
     r = GpuRAG2Retriever(org_id="t")
     with pytest.raises(RuntimeError, match="no CPU fallback"):

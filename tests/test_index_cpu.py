@@ -64,3 +64,16 @@ def test_pack_queries_and_algorithmic_bytes():
     df = idx.df
     want = sum(int(df[t]) * 8 + 8 * idx.n_blk for q in qs for t in q)
     assert idx.algorithmic_bytes(qs) == want
+
+
+def test_save_load_roundtrip(tmp_path):
+    doc, term, tf, L = _coo(2500, 200)
+    idx = BM25Index.build(doc, term, tf, L, 200, blk_docs=512)
+    f = tmp_path / "idx.pt"
+    idx.save(f)
+    back = BM25Index.load(f)
+    for name in ("skip", "postings", "df"):
+        assert torch.equal(getattr(idx, name), getattr(back, name))
+    assert torch.equal(idx.idf.view(torch.int32), back.idf.view(torch.int32))
+    assert (idx.n_docs, idx.blk_docs, idx.V, idx.nnz, idx.k1, idx.b, idx.avgdl) == \
+           (back.n_docs, back.blk_docs, back.V, back.nnz, back.k1, back.b, back.avgdl)

@@ -193,6 +193,7 @@ int thr_sync(thr_handle* h, void* stream) {
     st->code = 0;
     const char* what = code == THR_EOVERFLOW  ? "candidate buffer overflow"
                        : code == THR_ETIMEOUT ? "pipeline watchdog timeout (kernel trapped)"
+                       : code == THR_EINVAL   ? "invalid input detected on the device (tag 460: a BM25 query has more than 32 terms)"
                                               : "device-side failure";
     return thr_fail(h, code, "%s (kernel tag %d, detail %lld)%s%s", what, where, aux,
                     e != cudaSuccess ? "; CUDA: " : "", e != cudaSuccess ? cudaGetErrorString(e) : "");

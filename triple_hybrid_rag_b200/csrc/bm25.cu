@@ -483,9 +483,11 @@ __global__ void bm25_df_kernel(const int64_t* skip, int n_blk, int V, int64_t* d
 
 // cost[q] = total postings of the query's terms.
 __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, const int64_t* df, int V,
-                                 int B, unsigned long long* keys) {
+                                 int B, unsigned long long* keys, thr_dev_status* status) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
+  // more terms than the kernel has lanes for: reported by thr_sync, never silently truncated
+  if (q_off[q + 1] - q_off[q] > kMaxTerms) dev_report(status, THR_EINVAL, 460, q);
   long long c = 0;
   for (int i = q_off[q]; i < q_off[q + 1]; ++i) {
     int t = q_terms[i];
@@ -704,7 +706,7 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   uint64_t* part_keys = (uint64_t*)(ws + o_pkeys);
 
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
-  bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys);
+  bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys, h->d_status);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
   static int units_per_sm = 0;
   if (!units_per_sm) {

@@ -120,6 +120,21 @@ class BM25Index:
         return BM25Index(self.skip.to(device), self.postings.to(device), self.idf.to(device), self.df.to(device),
                          self.n_docs, self.blk_docs, self.V, self.nnz, self.k1, self.b, self.avgdl)
 
+    def save(self, path) -> None:
+        """Persist the index (one torch file; tensors are moved to the CPU).  SURVEY.md 8f row 1: the resident
+        index needs its own checkpoint so that a retriever can start without re-reading the corpus."""
+        torch.save({"format": "thr-bm25-v1", "skip": self.skip.cpu(), "postings": self.postings.cpu(),
+                    "idf": self.idf.cpu(), "df": self.df.cpu(), "n_docs": self.n_docs, "blk_docs": self.blk_docs,
+                    "V": self.V, "nnz": self.nnz, "k1": self.k1, "b": self.b, "avgdl": self.avgdl}, path)
+
+    @staticmethod
+    def load(path, device="cpu") -> "BM25Index":
+        d = torch.load(path, map_location="cpu", weights_only=True)
+        if d.get("format") != "thr-bm25-v1":
+            raise ValueError(f"{path}: not a BM25Index file")
+        return BM25Index(d["skip"], d["postings"], d["idf"], d["df"], int(d["n_docs"]), int(d["blk_docs"]),
+                         int(d["V"]), int(d["nnz"]), float(d["k1"]), float(d["b"]), float(d["avgdl"])).to(device)
+
     def algorithmic_bytes(self, queries: Sequence[Sequence[int]]) -> int:
         """sum over queries and terms of df_t * 8 B of postings + 8 B of skip entry per
         (term, range)."""

@@ -148,6 +148,40 @@ class ResidentIndex:
         self.token_store = None if token_store is None else token_store.to(torch.bfloat16).to(dev).contiguous()
         self.token_lens = None if token_lens is None else token_lens.to(torch.int32).to(dev).contiguous()
 
+    # ---- persistence: start a retriever without re-reading / re-embedding the corpus ----
+    def save(self, path) -> None:
+        torch.save({"format": "thr-resident-v1", "rows": self.rows, "parents": self.parents, "vocab": self.vocab,
+                    "X": self.X.cpu(), "token_store": None if self.token_store is None else self.token_store.cpu(),
+                    "token_lens": None if self.token_lens is None else self.token_lens.cpu(),
+                    "bm25": {"skip": self.bm25.skip.cpu(), "postings": self.bm25.postings.cpu(),
+                             "idf": self.bm25.idf.cpu(), "df": self.bm25.df.cpu(), "n_docs": self.bm25.n_docs,
+                             "blk_docs": self.bm25.blk_docs, "V": self.bm25.V, "nnz": self.bm25.nnz,
+                             "k1": self.bm25.k1, "b": self.bm25.b, "avgdl": self.bm25.avgdl}}, path)
+
+    @classmethod
+    def load(cls, engine: Engine, path) -> "ResidentIndex":
+        d = torch.load(path, map_location="cpu", weights_only=True)
+        if d.get("format") != "thr-resident-v1":
+            raise ValueError(f"{path}: not a ResidentIndex file")
+        self = cls.__new__(cls)
+        dev = engine.device
+        self.engine = engine
+        self.rows = d["rows"]
+        self.id_of = {r["child_id"]: i for i, r in enumerate(self.rows)}
+        self.parents = d["parents"]
+        self.collections = [r.get("collection") for r in self.rows]
+        self.vocab = d["vocab"]
+        self.X = d["X"].to(dev).contiguous()
+        engine.dense_index_set(self.X)
+        b = d["bm25"]
+        self.bm25 = BM25Index(b["skip"], b["postings"], b["idf"], b["df"], int(b["n_docs"]), int(b["blk_docs"]),
+                              int(b["V"]), int(b["nnz"]), float(b["k1"]), float(b["b"]), float(b["avgdl"])).to(dev)
+        engine.bm25_index_set(self.bm25.skip, self.bm25.postings, self.bm25.idf, self.bm25.n_docs, self.bm25.blk_docs,
+                              self.bm25.V)
+        self.token_store = None if d["token_store"] is None else d["token_store"].to(dev).contiguous()
+        self.token_lens = None if d["token_lens"] is None else d["token_lens"].to(dev).contiguous()
+        return self
+
     def row_dict(self, i: int, **extra) -> Dict[str, Any]:
         r = self.rows[i]
         d = {"child_id": r["child_id"], "parent_id": r["parent_id"], "document_id": r["document_id"],
