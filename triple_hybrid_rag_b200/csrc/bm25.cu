@@ -88,7 +88,7 @@ __device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t
   if (tid == 0) { *s_prefix = 0ull; *s_want = ksel; }
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
-    if (tid < 256) hist[tid] = 0;
+    for (int i = tid; i < 256; i += kConsumers) hist[i] = 0;
     bar_consumers();
     const uint64_t prefix = *s_prefix;
     for (int i = tid; i < n; i += kConsumers) {
