@@ -48,7 +48,7 @@ struct Posting { uint32_t doc; float imp; };
 
 // A work unit: one query restricted to the doc ranges [r0, r1).
 struct Unit { int q; int r0; int r1; unsigned cost; };
-constexpr int kMaxUnitsPerQuery = 16;
+constexpr int kMaxUnitsPerQuery = 64;    // small batches: one query can still spread over many SMs
 
 struct Bm25Args {
   const int64_t* skip;    // [V * n_blk + 1]
@@ -572,7 +572,7 @@ __global__ void bm25_order_kernel(const Unit* units, const int* total_units, int
 __global__ void __launch_bounds__(256) bm25_merge_kernel(const uint64_t* part_keys, const int32_t* part_cnt,
                                                          const int* unit_base, int k, int64_t id_base,
                                                          int64_t* out_ids, float* out_scores, int32_t* out_count) {
-  __shared__ uint64_t keys[kMaxUnitsPerQuery * kMaxSelB];
+  extern __shared__ uint64_t keys[];   // next power of two >= kMaxUnitsPerQuery * k
   const int q = blockIdx.x, tid = threadIdx.x;
   const int u0 = unit_base[q], u1 = unit_base[q + 1];
   const int slots = (u1 - u0) * k;
@@ -738,7 +738,11 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "bm25_kernel");
   tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
-  bm25_merge_kernel<<<B, 256, 0, s>>>(part_keys, part_cnt, unit_base, k, st->id_base, out_ids, out_scores, out_count);
+  size_t merge_slots = 32;
+  while (merge_slots < (size_t)kMaxUnitsPerQuery * k) merge_slots <<= 1;
+  THR_CUDA(h, cudaFuncSetAttribute(bm25_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(merge_slots * 8)));
+  bm25_merge_kernel<<<B, 256, merge_slots * 8, s>>>(part_keys, part_cnt, unit_base, k, st->id_base, out_ids, out_scores,
+                                                    out_count);
   thr_prof_end(h, tok, s);
   THR_CHECK_LAUNCH(h, "bm25_merge_kernel");
   return THR_OK;

@@ -668,7 +668,11 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64
   THR_REQUIRE(h, k + margin <= kMaxSel, "thr_dense_topk: k + margin = %d exceeds %d", k + margin, kMaxSel);
   THR_REQUIRE(h, Q && out_ids && out_scores && out_count, "thr_dense_topk: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
-  const int G = st->cta_group;
+  // up to 128 queries fit one CTA's M = 128 tile: the single-CTA kernel then does half the MMA work per
+  // chunk tile and the scan is HBM-bound (batch-1 latency); larger batches use the CTA pair (M = 256)
+  // (only while the finalize kernel's shared memory — one K' list per CTA — still fits)
+  const bool small_ok = (size_t)h->num_sms * (k + margin) * 8 + (size_t)st->D * 2 <= 200 * 1024;
+  const int G = (B <= kBlockM && small_ok) ? 1 : st->cta_group;
   const int64_t tiles = (st->N + kTileN - 1) / kTileN;
   int n_clusters = h->num_sms / G;
   if ((int64_t)n_clusters > tiles) n_clusters = (int)tiles;
