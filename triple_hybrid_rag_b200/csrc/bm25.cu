@@ -42,7 +42,7 @@ constexpr int kMaxBlkDocs = 2048;                // docs per range = accumulator
 constexpr int kMaxSelB = 256;
 constexpr int kCandCap = 2560;                   // >= kMaxBlkDocs + 2 * kMaxSelB
 constexpr int kStage = 272;                      // postings per warp staging buffer (two per warp)
-constexpr int kMaxRound = 8;                     // ranges per warp and round, at most
+constexpr int kMaxRound = 32;                    // ranges per warp and round, at most
 
 struct Posting { uint32_t doc; float imp; };
 
