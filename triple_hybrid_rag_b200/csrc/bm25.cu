@@ -42,6 +42,7 @@ constexpr int kMaxBlkDocs = 2048;                // docs per range = accumulator
 constexpr int kMaxSelB = 256;
 constexpr int kCandCap = 2560;                   // >= kMaxBlkDocs + 2 * kMaxSelB
 constexpr int kStage = 272;                      // postings per warp staging buffer (two per warp)
+constexpr int kSmallSeg = 48;                    // segments up to this many postings are staged first
 constexpr int kMaxRound = 32;                    // ranges per warp and round, at most
 
 struct Posting { uint32_t doc; float imp; };
@@ -274,17 +275,23 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       const int cnt = my_term >= 0 ? (int)(hi_l - lo_l) : 0;
       const int slack = (int)(lo_l & 1);                       // copies start at an even posting (16-byte granules)
       const int cp = cnt > 0 ? ((slack + cnt + 1) & ~1) : 0;   // postings copied
-      int incl = cp;
+      // Small segments first (they are most of the visits and the worst case for a global read), then the
+      // large ones in term order while room remains; each class is packed by a warp scan.
+      const bool small_seg = cnt > 0 && cp <= kSmallSeg;
+      int incl_s = small_seg ? cp : 0, incl_b = (cnt > 0 && !small_seg) ? cp : 0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+        const int vs = __shfl_up_sync(0xffffffffu, incl_s, d);
+        const int vb = __shfl_up_sync(0xffffffffu, incl_b, d);
+        if (lane >= d) { incl_s += vs; incl_b += vb; }
       }
-      const bool fits = cnt > 0 && incl <= kStage;             // a prefix of the terms (in order) is staged
-      const unsigned staged = __ballot_sync(0xffffffffu, fits);
-      int bytes = fits ? cp * 8 : 0;
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, sft);
+      const bool fits_s = small_seg && incl_s <= kStage;
+      const int used_s = (int)__reduce_max_sync(0xffffffffu, (unsigned)(fits_s ? incl_s : 0));
+      const bool fits_b = cnt > 0 && !small_seg && used_s + incl_b <= kStage;
+      const int used_b = (int)__reduce_max_sync(0xffffffffu, (unsigned)(fits_b ? incl_b : 0));
+      const bool fits = fits_s || fits_b;
+      const int incl = fits_s ? incl_s : used_s + incl_b;      // end of this lane's slot in the buffer
+      const int bytes = (used_s + used_b) * 8;
       const uint32_t bar = sbar_w + (seq_no & 1u) * 8u;
       fence_proxy_async_smem();   // this warp's earlier reads of the buffer precede the async writes
       if (lane == 0) {
@@ -301,7 +308,6 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
               "r"((uint32_t)cp * 8u), "r"(bar)
             : "memory");
       }
-      (void)staged;
       return fits ? off + slack : -1;
     };
     int cur_off = -1, nxt_off = -1;
