@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       p1 = __ldg(row + my_r0 + 1);
       p2 = my_n > 1 ? __ldg(row + my_r0 + 2) : p1;
     }
-    // Stage the postings [lo_l, hi_l) of every term (lane) into buffer (seq_no & 1).  Returns this lane's
-    // offset of its first posting inside the buffer, or -1 when its segment did not fit (read from global).
+    // Stage the postings [lo_l, hi_l) of every term (lane) into buffer (seq_no & 1).  Returns, packed, this
+    // lane's first staged posting and how many of its postings are staged (the rest is read from global).
     auto stage_issue = [&](int64_t lo_l, int64_t hi_l, uint32_t seq_no) -> int {
       const int cnt = my_term >= 0 ? (int)(hi_l - lo_l) : 0;
       const int slack = (int)(lo_l & 1);                       // copies start at an even posting (16-byte granules)
@@ -287,11 +287,13 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
       }
       const bool fits_s = small_seg && incl_s <= kStage;
       const int used_s = (int)__reduce_max_sync(0xffffffffu, (unsigned)(fits_s ? incl_s : 0));
-      const bool fits_b = cnt > 0 && !small_seg && used_s + incl_b <= kStage;
-      const int used_b = (int)__reduce_max_sync(0xffffffffu, (unsigned)(fits_b ? incl_b : 0));
-      const bool fits = fits_s || fits_b;
-      const int incl = fits_s ? incl_s : used_s + incl_b;      // end of this lane's slot in the buffer
-      const int bytes = (used_s + used_b) * 8;
+      const bool big = cnt > 0 && !small_seg;
+      const int slot0 = fits_s ? incl_s - cp : used_s + incl_b - cp;   // first buffer entry of this lane's copy
+      int st_cp = 0;                                                    // postings copied into the buffer
+      if (fits_s) st_cp = cp;
+      else if (big && slot0 + cp <= kStage) st_cp = cp;
+      else if (big && slot0 + 64 <= kStage) st_cp = (kStage - slot0) & ~1;   // the first one that does not fit: a prefix
+      const int bytes = (int)__reduce_add_sync(0xffffffffu, (unsigned)st_cp) * 8;
       const uint32_t bar = sbar_w + (seq_no & 1u) * 8u;
       fence_proxy_async_smem();   // this warp's earlier reads of the buffer precede the async writes
       if (lane == 0) {
@@ -299,18 +301,19 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
         else mbar_arrive(bar);
       }
       __syncwarp();
-      const int off = incl - cp;
-      if (fits) {
+      if (st_cp > 0) {
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
             :
-            : "r"(stage_w + ((seq_no & 1u) * kStage + (uint32_t)off) * 8u), "l"(a.post + (lo_l - slack)),
-              "r"((uint32_t)cp * 8u), "r"(bar)
+            : "r"(stage_w + ((seq_no & 1u) * kStage + (uint32_t)slot0) * 8u), "l"(a.post + (lo_l - slack)),
+              "r"((uint32_t)st_cp * 8u), "r"(bar)
             : "memory");
       }
-      return fits ? off + slack : -1;
+      // (first staged posting) | (number of staged postings) << 16
+      const int st_n = st_cp == cp ? cnt : max(0, st_cp - slack);
+      return (slot0 + slack) | (st_n << 16);
     };
-    int cur_off = -1, nxt_off = -1;
+    int cur_off = 0, nxt_off = 0;
     if (my_n > 0) cur_off = stage_issue(p0, p1, seq);
 
     // ---- round 0: a threshold to start from.  Every warp scores its first range and contributes only
@@ -353,61 +356,44 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
         mbar_wait(sbar_w + (seq & 1u) * 8u, (seq >> 1) & 1u, a.status, 450);
         const uint32_t sbuf = stage_w + (seq & 1u) * kStage * 8u;
         ++seq;
-        if (live) {
-          // pass 1: accumulate in term order
+        // One walk over the range's postings, term by term: the staged part of a segment from shared memory,
+        // the rest (what did not fit the staging buffer) from global with four chunks in flight.
+        auto walk = [&](const bool extract) {
           for (unsigned rem = live; rem; rem &= rem - 1) {
             const int g = __ffs(rem) - 1;
             const int n = __shfl_sync(0xffffffffu, cnt, g);
-            const int off = __shfl_sync(0xffffffffu, cur_off, g);
+            const int so = __shfl_sync(0xffffffffu, cur_off, g);
             const float w = __shfl_sync(0xffffffffu, my_w, g);
-            if (off >= 0) {
-              const uint32_t end = sbuf + (uint32_t)(off + n) * 8u;
-              for (uint32_t pa = sbuf + (uint32_t)(off + lane) * 8u; pa < end; pa += 256u) {
-                uint32_t doc;
-                float imp;
-                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(doc), "=f"(imp) : "r"(pa));
-                rmw(acc0, doc, __fmul_rn(w, imp));
-              }
-            } else {  // did not fit the staging buffer: four chunks in flight from global
-              const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
-              for (int i = lane; i < n; i += 128) {
+            const int st_n = so >> 16;
+            const uint32_t first = sbuf + (uint32_t)(so & 0xffff) * 8u;
+            const uint32_t end = first + (uint32_t)st_n * 8u;
+            for (uint32_t pa = first + lane * 8u; pa < end; pa += 256u) {
+              uint32_t doc;
+              float imp;
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(doc), "=f"(imp) : "r"(pa));
+              if (extract) take(acc0, doc); else rmw(acc0, doc, __fmul_rn(w, imp));
+            }
+            if (st_n < n) {
+              const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g) + st_n;
+              const int m = n - st_n;
+              for (int i = lane; i < m; i += 128) {
                 uint2 pp[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (i + 32 * u < n) pp[u] = ldg_posting(seg + i + 32 * u);
+                  if (i + 32 * u < m) pp[u] = ldg_posting(seg + i + 32 * u);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (i + 32 * u < n) rmw(acc0, pp[u].x, __fmul_rn(w, __uint_as_float(pp[u].y)));
+                  if (i + 32 * u < m) {
+                    if (extract) take(acc0, pp[u].x); else rmw(acc0, pp[u].x, __fmul_rn(w, __uint_as_float(pp[u].y)));
+                  }
               }
             }
             __syncwarp();  // the same doc may recur in the next term
           }
-          // pass 2: first visit of a doc takes its final score and zeroes the slot
-          for (unsigned rem = live; rem; rem &= rem - 1) {
-            const int g = __ffs(rem) - 1;
-            const int n = __shfl_sync(0xffffffffu, cnt, g);
-            const int off = __shfl_sync(0xffffffffu, cur_off, g);
-            if (off >= 0) {
-              const uint32_t end = sbuf + (uint32_t)(off + n) * 8u;
-              for (uint32_t pa = sbuf + (uint32_t)(off + lane) * 8u; pa < end; pa += 256u) {
-                uint32_t doc;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(doc) : "r"(pa));
-                take(acc0, doc);
-              }
-            } else {
-              const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g);
-              for (int i = lane; i < n; i += 128) {
-                uint32_t dd[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (i + 32 * u < n) dd[u] = ldg_posting(seg + i + 32 * u).x;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (i + 32 * u < n) take(acc0, dd[u]);
-              }
-            }
-            __syncwarp();
-          }
+        };
+        if (live) {
+          walk(false);   // pass 1: accumulate in term order
+          walk(true);    // pass 2: first visit of a doc takes its final score and zeroes the slot
         }
         // this term's postings three ranges ahead -> L2 (the staging copy then hits L2, not DRAM)
         if (p3 > p2) {
