@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
-for f in tests/test_gpu_fuse.py tests/test_gpu_bm25.py tests/test_gpu_maxsim.py tests/test_gpu_dense.py tests/test_gpu_retriever.py tests/test_gpu_fullsize.py "$@"; do
+for f in tests/test_gpu_fuse.py tests/test_gpu_bm25.py tests/test_gpu_maxsim.py tests/test_gpu_dense.py tests/test_gpu_retriever.py tests/test_gpu_fullsize.py tests/test_gpu_edges.py "$@"; do
   n=$(basename $f .py)
   timeout 600 python -m pytest $f -q -m gpu -p no:cacheprovider --timeout 120 > gpurun_out/$n.log 2>&1
   r=$?

@@ -196,13 +196,16 @@ class Engine:
             rerank = self._dev(rerank, torch.float64, "rerank")
             has_rerank = self._dev(has_rerank, torch.uint8, "has_rerank")
         B = off.numel() - 1
-        keep = torch.zeros((max(rrf.numel(), 1),), dtype=torch.uint8, device=self.device)
+        n = rrf.numel()
+        if n == 0:  # a zero-size tensor has a NULL data pointer; the C side wants a valid (unread) address
+            rrf = torch.zeros((1,), dtype=torch.float64, device=self.device)
+        keep = torch.zeros((max(n, 1),), dtype=torch.uint8, device=self.device)
         refused = torch.empty((B,), dtype=torch.uint8, device=self.device)
         mx = torch.empty((B,), dtype=torch.float64, device=self.device)
         self._check(self._lib.thr_safety(self._h, B, _ptr(off), _ptr(rerank), _ptr(has_rerank), _ptr(rrf),
                                          float(threshold), float(alpha), int(top_k), _ptr(keep), _ptr(refused),
                                          _ptr(mx), self._stream()))
-        return keep[: rrf.numel()], refused, mx
+        return keep[:n], refused, mx
 
     # -- K4 MaxSim --------------------------------------------------------------------------
     def maxsim(self, Qtok: torch.Tensor, Dtok: torch.Tensor, cand: torch.Tensor,
