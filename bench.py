@@ -316,6 +316,11 @@ def main():
             lat1.append(time.perf_counter() - s0)
     clk = clocks.stop()
 
+    stages_all = None
+    if world > 1:  # every rank's per-kernel times (the step is as slow as the slowest shard)
+        mine = {n: round(ms / max(c, 1), 4) for n, (ms, c) in prof.items()}
+        stages_all = [None] * world
+        dist.all_gather_object(stages_all, mine, group=group)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -348,6 +353,7 @@ def main():
         "clocks": clk,
         "latency": {"p50_ms_batch256_e2e": statistics.median(lat) * 1e3, "p50_ms_batch1_e2e": statistics.median(lat1) * 1e3},
         "stages_ms": stages,
+        **({"stages_ms_per_rank": stages_all} if stages_all else {}),
         "roofline": {"kernel": "dense_score_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained,
                      "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None,
                      "traffic": traffic.get("dense_score_kernel", {}).get("dram_bytes_per_launch"),

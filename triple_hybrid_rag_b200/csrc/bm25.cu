@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   int* q_term = (int*)(hist + 256);                                           // kMaxTerms
   float* q_idf = (float*)(q_term + kMaxTerms);                                // kMaxTerms
   unsigned long long* s_prefix = (unsigned long long*)(q_idf + kMaxTerms);
-  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=unit [4]=nterms [5]=overflow
+  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=unit [4]=nterms [5]=overflow [6]=bound
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < kWarps * kMaxBlkDocs; i += kThreads) acc[i] = 0.f;
@@ -405,37 +405,75 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
         cur_off = nxt_off;
       }
 
-      // ---- round barrier: overflow roll-back, compaction ----
+      // ---- round barrier: overflow roll-back, compaction, size of the next round ----
       __syncthreads();
-      if (*v_ovf) {
-        // Discard this round's appends, then redo its ranges one warp and one range at a time (all
-        // accumulators are zero again: pass 2 zeroes even when an append is dropped).
-        __syncthreads();
+      const int cnt_round_end = *v_cnt;      // stable until the next barrier (may exceed the capacity after an overflow)
+      const bool overflowed = *v_ovf != 0;
+      __syncthreads();
+      if (overflowed) {
+        // Discard this round's appends and redo its ranges in sub-rounds of ONE range per warp, all warps
+        // in parallel from global memory (the accumulators are zero again: pass 2 zeroes even when an append
+        // is dropped).  Before each sub-round the warps add up how many docs they can append at most; if that
+        // does not fit even after a compaction, the sub-round runs one warp at a time (a single range
+        // appends at most 2048 <= capacity - k).
         if (tid == 0) { s_int[2] = cnt_round_start; s_int[5] = 0; }
         __syncthreads();
-        for (int wsel = 0; wsel < kWarps; ++wsel) {
-          for (int jj = 0; jj < todo; ++jj) {
-            const bool need = *v_cnt + kMaxBlkDocs > kCandCap;  // count is stable here; true implies count > k
-            __syncthreads();                                      // everyone has read it before anyone appends
-            if (need) compact();
-            const int j = done + jj;
-            if (warp == wsel && j < my_n) {
-              const int r = my_r0 + j;
-              const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;
-              int64_t lo_l = 0, hi_l = 0;
-              if (my_term >= 0) { lo_l = __ldg(row + r); hi_l = __ldg(row + r + 1); }
+        for (int jj = 0; jj < todo; ++jj) {
+          const int j = done + jj;
+          const bool mine = j < my_n;
+          const int r = my_r0 + j;
+          const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;
+          int64_t lo_l = 0, hi_l = 0;
+          if (mine && my_term >= 0) { lo_l = __ldg(row + r); hi_l = __ldg(row + r + 1); }
+          int touched = (int)(hi_l - lo_l);
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, sft);
+          touched = min(touched, a.blk_docs);
+          if (tid == 0) s_int[6] = 0;
+          __syncthreads();
+          if (lane == 0) atomicAdd(&s_int[6], touched);
+          __syncthreads();
+          const int bound = s_int[6];
+          int cnt_now = *v_cnt;
+          __syncthreads();                       // everyone has read the counters before anyone changes them
+          if (cnt_now + bound > kCandCap && cnt_now > a.k) {
+            compact();
+            cnt_now = *v_cnt;
+            __syncthreads();
+          }
+          if (cnt_now + bound <= kCandCap) {
+            if (mine) {
               slots_from_global(r, 0, acc0, lo_l, hi_l, 0);
               slots_from_global(r, 0, acc0, lo_l, hi_l, 1);
             }
             __syncthreads();
+          } else {
+            for (int wsel = 0; wsel < kWarps; ++wsel) {
+              const bool need = *v_cnt + kMaxBlkDocs > kCandCap;  // stable here; true implies count > k
+              __syncthreads();
+              if (need) compact();
+              if (warp == wsel && mine) {
+                slots_from_global(r, 0, acc0, lo_l, hi_l, 0);
+                slots_from_global(r, 0, acc0, lo_l, hi_l, 1);
+              }
+              __syncthreads();
+            }
           }
         }
         if (*v_ovf) dev_report(a.status, THR_EOVERFLOW, 440, *v_cnt);  // excluded by construction
+        __syncthreads();
       }
       // uniform after the barrier; early rounds compact sooner: a good threshold early saves appends later
       if (*v_cnt > (per_round <= 4 ? max(2 * a.k, 256) : kCandCap / 2)) compact();
       done += todo;
-      if (per_round < kMaxRound) per_round *= 2;
+      // Next round: twice as long, but no longer than what the appends of this round (per range and warp)
+      // predict to fill half of the free candidate slots — an overflow costs a whole redo.
+      {
+        const int appended = max(overflowed ? kCandCap : cnt_round_end - cnt_round_start, 1);
+        const int room = max(kCandCap - *v_cnt, 0) / 2;
+        const long long fit = (long long)room * todo / appended;
+        per_round = (int)max(1ll, min((long long)min(2 * per_round, kMaxRound), fit));
+      }
       __syncthreads();
     }
 
