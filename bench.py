@@ -266,18 +266,38 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(max(args.warmup, 3)):
-        searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+    # Warm-up: at least W (>= 3) steps AND at least ~0.4 s of back-to-back steps, so that clocks, NCCL channels
+    # and lazily loaded kernels are in their steady state before the timed region (short steps — small shards —
+    # otherwise start timing while the GPU is still ramping up from idle clocks).
+    def run_steps(n):
+        for _ in range(n):
+            searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+        eng.sync()
+
+    n_warm = max(args.warmup, 3)
+    run_steps(n_warm)
+    t_w = time.perf_counter()
+    run_steps(3)
+    extra = torch.tensor([min(2000, int(0.4 / max((time.perf_counter() - t_w) / 3, 1e-5)))], dtype=torch.int64, device=dev)
+    if world > 1:  # the step contains a collective: every rank must run the same number of steps
+        dist.broadcast(extra, 0, group=group)
+    run_steps(int(extra.item()))
+    n_warm += 3 + int(extra.item())
     eng.sync()
+    clocks.mark()
     eng.prof_reset()
     l0 = eng.launches
     barrier()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         out = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+        step_ev[i].record()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    marks = [ev0] + step_ev
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     prof = eng.prof_read()
     eng.prof_enable(False)
     launches = eng.launches - l0
@@ -345,13 +365,15 @@ def main():
     bm25_ms = stages.get("bm25", 0.0)
     line = {
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": make_config(args, world),
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clk,
         "latency": {"p50_ms_batch256_e2e": statistics.median(lat) * 1e3, "p50_ms_batch1_e2e": statistics.median(lat1) * 1e3},
+        "step_ms": {"p50": statistics.median(per_step), "min": min(per_step), "max": max(per_step),
+                    "argmax": per_step.index(max(per_step))},
         "stages_ms": stages,
         **({"stages_ms_per_rank": stages_all} if stages_all else {}),
         "roofline": {"kernel": "dense_score_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained,

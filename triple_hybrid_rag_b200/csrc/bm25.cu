@@ -82,49 +82,74 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// Block-cooperative: keep the ksel largest of keys[0..n) in place, n > ksel.
+// Barrier among the first kNT threads of the CTA (named barrier kBar; kBar 0 with kNT = blockDim is __syncthreads).
+template <int kNT, int kBar>
+__device__ __forceinline__ void bar_group() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kNT) : "memory");
+}
+
+// Cooperative among kNT threads: keep the ksel largest of keys[0..n) in place, n > ksel, n <= kCap.
 // Returns the ksel-th largest key.  hist/scal are shared scratch.
-__device__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t* hist,
-                                       unsigned long long* s_prefix, int* s_want, int* s_cnt, int tid) {
+template <int kNT, int kCap, int kBar>
+__device__ uint64_t block_compact_topk_t(uint64_t* keys, int n, int ksel, uint32_t* hist,
+                                         unsigned long long* s_prefix, int* s_want, int* s_cnt, int tid) {
   if (tid == 0) { *s_prefix = 0ull; *s_want = ksel; }
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
-    for (int i = tid; i < 256; i += kConsumers) hist[i] = 0;
-    bar_consumers();
+    for (int i = tid; i < 256; i += kNT) hist[i] = 0;
+    bar_group<kNT, kBar>();
     const uint64_t prefix = *s_prefix;
-    for (int i = tid; i < n; i += kConsumers) {
+    for (int i = tid; i < n; i += kNT) {
       const uint64_t key = keys[i];
       const bool match = pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8));
       if (match) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
     }
-    bar_consumers();
-    if (tid == 0) {
-      int want = *s_want, cum = 0, d = 255;
-      for (; d > 0; --d) {
-        if (cum + (int)hist[d] >= want) break;
-        cum += hist[d];
+    bar_group<kNT, kBar>();
+    // Find the digit that holds the want-th largest key: warp 0 walks the 256 bins from the top, 8 bins per lane
+    // plus a warp scan (a single thread walking them costs ~100 dependent shared-memory loads per pass).
+    if (tid < 32) {
+      const int want = *s_want;
+      int h[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { h[i] = (int)hist[255 - 8 * tid - i]; sum += h[i]; }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (tid >= d) incl += v;
       }
-      *s_want = want - cum;
-      *s_prefix = prefix | ((unsigned long long)d << shift);
+      int cum = incl - sum;
+      if (cum < want && want <= incl) {        // exactly one lane: the keys counted so far total >= want
+        int d = 255 - 8 * tid;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+          if (cum + h[i] < want && d == 255 - 8 * tid - i) { cum += h[i]; --d; }
+        *s_want = want - cum;
+        *s_prefix = prefix | ((unsigned long long)d << shift);
+      }
     }
-    bar_consumers();
+    bar_group<kNT, kBar>();
   }
   const uint64_t T = *s_prefix;
   // survivors: read everything first, then rewrite the front
-  constexpr int kPer = (kCandCap + kConsumers - 1) / kConsumers;
+  constexpr int kPer = (kCap + kNT - 1) / kNT;
   uint64_t mine[kPer];
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
-    int i = tid + j * kConsumers;
+    int i = tid + j * kNT;
     mine[j] = i < n ? keys[i] : 0ull;
   }
   if (tid == 0) *s_cnt = 0;
-  bar_consumers();
+  bar_group<kNT, kBar>();
 #pragma unroll
   for (int j = 0; j < kPer; ++j)
     if (mine[j] >= T && mine[j] != 0ull) keys[atomicAdd(s_cnt, 1)] = mine[j];
-  bar_consumers();
+  bar_group<kNT, kBar>();
   return T;
+}
+__device__ __forceinline__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t* hist,
+                                                       unsigned long long* s_prefix, int* s_want, int* s_cnt, int tid) {
+  return block_compact_topk_t<kConsumers, kCandCap, 0>(keys, n, ksel, hist, s_prefix, s_want, s_cnt, tid);
 }
 
 constexpr size_t kSmemAcc = (size_t)kWarps * kMaxBlkDocs * 4;
@@ -505,6 +530,367 @@ __global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Span kernel: the CTA, not the warp, owns the accumulator.
+//
+// A span is kSpanDocs consecutive docs (a whole number of skip ranges) with one fp32 accumulator slot per doc
+// in shared memory.  A term's postings inside a span are ONE contiguous piece of the term-major posting array
+// (skip[t][first range] .. skip[t][last range + 1]), so the producer warp streams it into a ring of kChunk-posting
+// stages with cp.async.bulk, one descriptor per chunk; all per-(term, span) bookkeeping lives in that one warp.
+// The kSpanThreads consumer threads do nothing but: wait for a chunk, add its postings (<= 2 per thread, docs of
+// one term are distinct: no atomics), release the stage.  Terms are separated by a named barrier (fp32 adds in
+// query order: the sum is part of the definition); after the span's last chunk the accumulator is scanned
+// with 16-byte loads: nonzero slots are zeroed and scores above tau are appended to the candidate list.
+// An append that does not fit leaves its slot in place and raises a flag; the list is then compacted (which raises
+// tau) and the scan repeats, so no threshold warm-up is needed for correctness.  Two CTAs share an SM, so the
+// barrier waits of one overlap with the work of the other.
+#ifndef THR_SPAN_DOCS
+#define THR_SPAN_DOCS 32768
+#endif
+#ifndef THR_SPAN_WARPS
+#define THR_SPAN_WARPS 16
+#endif
+#ifndef THR_SPAN_CHUNK
+#define THR_SPAN_CHUNK 1024
+#endif
+#ifndef THR_SPAN_STAGES
+#define THR_SPAN_STAGES 8
+#endif
+#ifndef THR_SPAN_CAP
+#define THR_SPAN_CAP 2048
+#endif
+#ifndef THR_SPAN_CTAS
+#define THR_SPAN_CTAS 1
+#endif
+constexpr int kSpanDocs = THR_SPAN_DOCS;          // a multiple of 2048 (every legal blk_docs divides it)
+constexpr int kSpanWarps = THR_SPAN_WARPS;
+constexpr int kSpanThreads = kSpanWarps * 32;     // consumers; warp kSpanWarps is the producer
+constexpr int kChunk = THR_SPAN_CHUNK;            // postings per ring stage
+constexpr int kStages = THR_SPAN_STAGES;
+constexpr int kSpanCap = THR_SPAN_CAP;            // candidate slots
+constexpr int kSpanCtas = THR_SPAN_CTAS;          // CTAs per SM
+constexpr int kSpanBar = 1;                       // named barrier of the consumers
+constexpr int kPerThread = kChunk / kSpanThreads; // postings per consumer thread and chunk
+constexpr int kScanIters = kSpanDocs / (4 * kSpanThreads);
+constexpr int kIssue = kStages / 2 < 1 ? 1 : kStages / 2;   // chunks the producer issues per round (half the ring)
+constexpr int kScanBatch = kScanIters < 8 ? kScanIters : 8;
+static_assert(kScanIters % kScanBatch == 0, "scan batches");
+static_assert(kChunk % kSpanThreads == 0 && kChunk % 2 == 0 && kPerThread >= 1 && kPerThread <= 8, "chunk shape");
+static_assert(kSpanDocs % kMaxBlkDocs == 0 && kSpanDocs % (4 * kSpanThreads) == 0, "span shape");
+static_assert(kSpanThreads >= kMaxSelB / 2, "the final sort uses kMaxSelB / 2 threads");
+static_assert(kSpanCap >= 2 * kMaxSelB + 256, "a compaction must free a useful part of the list");
+
+enum : uint32_t { kFNewUnit = 1u, kFSync = 2u, kFEndSpan = 4u, kFEndUnit = 8u, kFExit = 16u };
+
+constexpr size_t kSpanSmem = (size_t)kSpanDocs * 4 + (size_t)kSpanCap * 8 + (size_t)kStages * kChunk * 8 +
+                             kStages * 16 + 2 * kStages * 8 + 256 * 4 + 64 + 256;
+static_assert(kSpanCtas * (kSpanSmem + 1024) <= 233472, "kSpanCtas CTAs per SM");
+
+__global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel(const Bm25Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* acc = (float*)gen;                                                   // [kSpanDocs]
+  uint64_t* cand = (uint64_t*)(acc + kSpanDocs);                              // [kSpanCap]
+  Posting* ring = (Posting*)(cand + kSpanCap);                               // [kStages][kChunk]
+  uint4* desc = (uint4*)(ring + kStages * kChunk);                            // [kStages]
+  uint64_t* full = (uint64_t*)(desc + kStages);                               // [kStages]
+  uint64_t* empty = full + kStages;                                           // [kStages]
+  uint32_t* hist = (uint32_t*)(empty + kStages);                              // 256
+  unsigned long long* s_prefix = (unsigned long long*)(hist + 256);
+  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=overflow
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < kSpanDocs; i += kSpanThreads + 32) acc[i] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), kSpanWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_int[2] = 0;
+    s_int[3] = 0;
+  }
+  __syncthreads();
+  const uint32_t ring_u = smem_u32(ring), desc_u = smem_u32(desc), full_u = smem_u32(full), empty_u = smem_u32(empty);
+  const int spr = kSpanDocs / a.blk_docs;   // ranges per span
+
+  if (warp == kSpanWarps) {
+    // ================= producer: lane t <-> query term t =================
+    uint32_t s = 0, ph = 0;
+    auto put = [&](uint32_t x, uint32_t y, uint32_t z, uint32_t w, const Posting* src, uint32_t bytes) {
+      mbar_wait_relaxed(empty_u + s * 8u, ph ^ 1u, a.status, 470);
+      if (lane == 0) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + s * 16u), "r"(x), "r"(y), "r"(z), "r"(w)
+                     : "memory");
+#ifdef THR_ABL_NOCOPY
+        if (false) {
+#else
+        if (bytes) {
+#endif
+          mbar_arrive_expect_tx(full_u + s * 8u, bytes);
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              :
+              : "r"(ring_u + s * (uint32_t)(kChunk * 8)), "l"(src), "r"(bytes), "r"(full_u + s * 8u)
+              : "memory");
+        } else {
+          mbar_arrive(full_u + s * 8u);
+        }
+      }
+      __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1u; }
+    };
+    for (;;) {
+      int unit = -1;
+      if (lane == 0) {
+        const int w = atomicAdd(a.work_counter, 1);
+        unit = w < *a.total_units ? a.order[w] : -1;
+      }
+      unit = __shfl_sync(0xffffffffu, unit, 0);
+      if (unit < 0) break;
+      const int q = a.units[unit].q, r0 = a.units[unit].r0, r1 = a.units[unit].r1;
+      const int qlo = a.q_off[q];
+      const int nt = min(a.q_off[q + 1] - qlo, kMaxTerms);   // the host rejects longer queries
+      int term = -1;
+      float wgt = 0.f;
+      if (lane < nt) {
+        term = a.q_terms[qlo + lane];
+        if (term < 0 || term >= a.V) term = -1; else wgt = a.idf[term];
+      }
+      const int64_t* row = a.skip + (size_t)(term < 0 ? 0 : term) * a.n_blk;
+      auto edge = [&](int i) -> int64_t {   // first posting of this lane's term at the start of span i of the unit
+        return term >= 0 ? __ldg(row + min(r0 + i * spr, r1)) : 0;
+      };
+      const int nsp = (r1 - r0 + spr - 1) / spr;
+      int64_t e0 = edge(0), e1 = edge(1), e2 = edge(2), e3 = edge(3);
+      bool first = true;
+      for (int sp = 0; sp < nsp; ++sp) {
+        const int64_t e4 = edge(sp + 4);
+        // the span after the next one -> L2 (the ring then pulls from L2, not DRAM); capped per term
+#ifndef THR_ABL_NOPF
+        if (e3 > e2)
+#else
+        if (false)
+#endif
+        {
+          const int64_t b = e2 & ~(int64_t)1;
+          const int64_t nby = min((e3 - b) * 8, (int64_t)32768);
+          prefetch_l2_bulk(a.post + b, (uint32_t)((nby + 15) & ~(int64_t)15));
+        }
+        const int cnt = (int)(e1 - e0);
+        const unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+        if (live) {
+          const uint32_t doc0 = (uint32_t)(r0 + sp * spr) << a.blk_shift;
+          const int first_live = __ffs(live) - 1;
+          // Chunks of this span, generated lane-parallel.  Term t (lane t) owns nch chunks: the first one ends at a
+          // chunk boundary of the posting array's even-aligned copy grid (m0 postings), the others are whole.
+          const int slack_l = (int)(e0 & 1);
+          const int m0_l = min(cnt, kChunk - slack_l);
+          const int nch = cnt > 0 ? 1 + (cnt - m0_l + kChunk - 1) / kChunk : 0;
+          int incl = nch;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          for (int j0 = 0; j0 < total; j0 += kIssue) {      // rounds of kIssue chunks, one chunk per lane
+            const int j = j0 + lane;
+            int t = 0;                                      // term of chunk j = number of terms whose chunks end at or before j
+            for (int u = 0; u < nt; ++u) t += (__shfl_sync(0xffffffffu, incl, u) <= j) ? 1 : 0;
+            t = min(t, 31);
+            const int incl_t = __shfl_sync(0xffffffffu, incl, t);
+            const int nch_t = __shfl_sync(0xffffffffu, nch, t);
+            const int cnt_t = __shfl_sync(0xffffffffu, cnt, t);
+            const int64_t p_t = __shfl_sync(0xffffffffu, (long long)e0, t);
+            const uint32_t w_t = __float_as_uint(__shfl_sync(0xffffffffu, wgt, t));
+            const bool act = lane < kIssue && j < total;
+            if (act) {
+              const int c = j - (incl_t - nch_t);           // chunk index inside the term
+              const int sl_t = (int)(p_t & 1);
+              const int m0 = min(cnt_t, kChunk - sl_t);
+              const int slack = c == 0 ? sl_t : 0;
+              const int64_t p = c == 0 ? p_t : p_t + m0 + (int64_t)(c - 1) * kChunk;
+              const int m = c == 0 ? m0 : min(kChunk, cnt_t - m0 - (c - 1) * kChunk);
+              uint32_t fl = 0;
+              if (first && j == 0) fl |= kFNewUnit;
+              if (c == 0 && t != first_live) fl |= kFSync;
+              if (j == total - 1) fl |= kFEndSpan;
+              uint32_t st = s + (uint32_t)lane, php = ph;
+              if (st >= (uint32_t)kStages) { st -= kStages; php ^= 1u; }
+              mbar_wait_relaxed(empty_u + st * 8u, php ^ 1u, a.status, 472);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + st * 16u),
+                           "r"((uint32_t)m | ((uint32_t)slack << 16) | (fl << 24)), "r"(w_t), "r"(doc0), "r"((uint32_t)unit)
+                           : "memory");
+              const uint32_t bytes = (uint32_t)((slack + m + 1) & ~1) * 8u;
+              mbar_arrive_expect_tx(full_u + st * 8u, bytes);
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :
+                  : "r"(ring_u + st * (uint32_t)(kChunk * 8)), "l"(a.post + (p - slack)), "r"(bytes), "r"(full_u + st * 8u)
+                  : "memory");
+            }
+            __syncwarp();
+            s += (uint32_t)min(kIssue, total - j0);
+            if (s >= (uint32_t)kStages) { s -= kStages; ph ^= 1u; }
+          }
+          first = false;
+        }
+        e0 = e1; e1 = e2; e2 = e3; e3 = e4;
+      }
+      put(((first ? kFNewUnit : 0u) | kFEndUnit) << 24, 0u, 0u, (uint32_t)unit, nullptr, 0u);
+    }
+    put(kFExit << 24, 0u, 0u, 0u, nullptr, 0u);
+    return;
+  }
+
+  // ================= consumers =================
+  const uint32_t acc_u = smem_u32(acc);
+  volatile int* v_cnt = &s_int[2];
+  volatile int* v_ovf = &s_int[3];
+  float tau = 0.f;
+  int unit = -1;
+  uint32_t s = 0, ph = 0;
+  auto compact = [&](int n) {
+    const uint64_t T = block_compact_topk_t<kSpanThreads, kSpanCap, kSpanBar>(cand, n, a.k, hist, s_prefix, &s_int[0],
+                                                                              &s_int[1], tid);
+    // one ulp below the k-th best score: a later doc that ties with it but has a smaller id must still pass "> tau"
+    tau = f32_from_orderable((uint32_t)(T >> 32) - 1u);
+    if (tid == 0) { s_int[2] = s_int[1]; s_int[3] = 0; }
+    bar_group<kSpanThreads, kSpanBar>();
+  };
+  for (;;) {
+    mbar_wait(full_u + s * 8u, ph, a.status, 471);
+    uint32_t dx, dy, dz, dw;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dx), "=r"(dy), "=r"(dz), "=r"(dw) : "r"(desc_u + s * 16u));
+    const uint32_t fl = dx >> 24;
+    const int count = (int)(dx & 0xffffu);
+    if (fl & kFNewUnit) { unit = (int)dw; tau = 0.f; }
+    if (fl & kFSync) bar_group<kSpanThreads, kSpanBar>();     // the previous term's adds are complete
+#ifdef THR_ABL_NOADD
+    if (false) {
+#else
+    if (count > 0) {
+#endif
+      const float w = __uint_as_float(dy);
+      const uint32_t acc0 = acc_u - dz * 4u;                  // &acc[doc - doc0] == acc0 + doc * 4
+      const uint32_t pa = ring_u + s * (uint32_t)(kChunk * 8) + (((dx >> 16) & 1u) + (uint32_t)tid) * 8u;
+      uint32_t d[kPerThread];
+      float im[kPerThread], o[kPerThread];
+#pragma unroll
+      for (int u = 0; u < kPerThread; ++u) {
+        d[u] = 0; im[u] = 0.f;
+        if (tid + u * kSpanThreads < count)
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(d[u]), "=f"(im[u]) : "r"(pa + (uint32_t)u * (kSpanThreads * 8u)));
+      }
+#pragma unroll
+      for (int u = 0; u < kPerThread; ++u) {
+        o[u] = 0.f;
+        if (tid + u * kSpanThreads < count) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o[u]) : "r"(acc0 + d[u] * 4u));
+      }
+#pragma unroll
+      for (int u = 0; u < kPerThread; ++u)
+        if (tid + u * kSpanThreads < count)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc0 + d[u] * 4u), "f"(__fadd_rn(o[u], __fmul_rn(w, im[u]))) : "memory");
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_u + s * 8u);
+    if (++s == kStages) { s = 0; ph ^= 1u; }
+
+#ifdef THR_ABL_NOSCAN
+    if (false) {
+#else
+    if (fl & kFEndSpan) {
+#endif
+      bar_group<kSpanThreads, kSpanBar>();                    // every add of the span has landed
+      for (;;) {
+        const uint32_t sa = acc_u + (uint32_t)tid * 16u;
+        const uint32_t tau_u = tau > 0.f ? __float_as_uint(tau) : 0u;
+        // groups of kScanBatch 16-byte loads in flight, then the tests (the loads of a group do not wait for the
+        // stores of the previous slot)
+#pragma unroll 1
+        for (int j0 = 0; j0 < kScanIters; j0 += kScanBatch) {
+          uint32_t vv[kScanBatch][4];
+#pragma unroll
+          for (int u = 0; u < kScanBatch; ++u)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(vv[u][0]), "=r"(vv[u][1]), "=r"(vv[u][2]), "=r"(vv[u][3])
+                         : "r"(sa + (uint32_t)(j0 + u) * (kSpanThreads * 16u)));
+#pragma unroll
+          for (int u = 0; u < kScanBatch; ++u) {
+          const int j = j0 + u;
+          const uint32_t addr = sa + (uint32_t)j * (kSpanThreads * 16u);
+          const uint32_t(&v)[4] = vv[u];
+          // Scores are >= 0, so their bit patterns order like unsigned integers: one integer max of the four slots
+          // decides "all zero" (nothing to do), "none above tau" (zero the slots) or the rare append path, which
+          // repeats the test exactly in fp32 (a negative score, possible only with a caller-made negative idf,
+          // looks large here and is sorted out there).
+          const uint32_t m = max(max(v[0], v[1]), max(v[2], v[3]));
+          if (m > tau_u) {
+            uint32_t z[4] = {0u, 0u, 0u, 0u};
+            const uint32_t doc = dz + ((uint32_t)j * kSpanThreads + (uint32_t)tid) * 4u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float x = __uint_as_float(v[c]);
+              if (x > tau) {
+                const int pos = atomicAdd(&s_int[2], 1);
+                if (pos < kSpanCap) cand[pos] = pack_key(x, doc + c);
+                else { *v_ovf = 1; z[c] = v[c]; }              // stays in the accumulator for the next scan
+              }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3])
+                         : "memory");
+          } else if (m != 0u) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+          }
+          }
+        }
+        bar_group<kSpanThreads, kSpanBar>();
+        const int n = min(*v_cnt, kSpanCap);
+        const bool ovf = *v_ovf != 0;
+        if (!ovf && n <= kSpanCap / 2) break;                 // uniform: the counters are stable here
+        bar_group<kSpanThreads, kSpanBar>();                  // everyone has read them
+        if (n > a.k) compact(n);
+        else if (tid == 0) s_int[3] = 0;                      // (cannot overflow with n <= k; keep the flag sane)
+        if (!ovf) break;
+      }
+    }
+    if (fl & kFEndUnit) {
+      bar_group<kSpanThreads, kSpanBar>();
+      int n = min(*v_cnt, kSpanCap);
+      bar_group<kSpanThreads, kSpanBar>();
+      if (n > a.k) {
+        (void)block_compact_topk_t<kSpanThreads, kSpanCap, kSpanBar>(cand, n, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
+        n = s_int[1];
+        bar_group<kSpanThreads, kSpanBar>();
+      }
+      // bitonic sort (descending) of <= 256 keys padded with 0
+      for (int i = n + tid; i < kMaxSelB; i += kSpanThreads) cand[i] = 0ull;
+      bar_group<kSpanThreads, kSpanBar>();
+      for (int size = 2; size <= kMaxSelB; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          if (tid < kMaxSelB / 2) {
+            const int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
+            const int hi = lo + stride;
+            const bool desc_block = ((lo & size) == 0);
+            const uint64_t x = cand[lo], y = cand[hi];
+            const bool swap = desc_block ? (y > x) : (x > y);
+            if (swap) { cand[lo] = y; cand[hi] = x; }
+          }
+          bar_group<kSpanThreads, kSpanBar>();
+        }
+      }
+      if (tid == 0) a.part_cnt[unit] = n;
+      for (int i = tid; i < n; i += kSpanThreads) a.part_keys[(size_t)unit * a.k + i] = cand[i];
+      bar_group<kSpanThreads, kSpanBar>();
+      if (tid == 0) { s_int[2] = 0; s_int[3] = 0; }
+      bar_group<kSpanThreads, kSpanBar>();
+    }
+    if (fl & kFExit) break;
+  }
+}
+
 __global__ void bm25_df_kernel(const int64_t* skip, int n_blk, int V, int64_t* df) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V) return;
@@ -530,6 +916,8 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
 // per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
 constexpr unsigned long long kRangeCostDefault = 96;
+constexpr unsigned long long kSpanRangeCost = 200;   // span kernel: the scan of a range is worth about this many postings
+constexpr int kSpanUnitsPerCta = 2;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_slots, unsigned long long kRangeCost,
                                                           Unit* units, int* unit_base,
@@ -738,18 +1126,22 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys, h->d_status);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
-  static int units_per_sm = 0;
-  if (!units_per_sm) {
-    const char* e = getenv("THR_BM25_UNITS_PER_SM");
-    units_per_sm = e ? atoi(e) : 1;  // measured: 1 beats 2..5 at 1.25M and 10M docs (fewer threshold warm-ups)
-    if (units_per_sm < 1) units_per_sm = 1;
-  }
+  // Which kernel: the span kernel (CTA-owned accumulator, 2 CTAs per SM) unless THR_BM25_IMPL=warp asks for the
+  // warp-autonomous one.  Work is cut into about `slots` units of equal cost (heaviest first, fetched dynamically).
+  static int impl_span = -1, units_per_cta = 0;
   static long long range_cost = -1;
-  if (range_cost < 0) {
-    const char* e = getenv("THR_BM25_RANGE_COST");
-    range_cost = e ? atoll(e) : (long long)kRangeCostDefault;
+  if (impl_span < 0) {
+    const char* e = getenv("THR_BM25_IMPL");
+    impl_span = (e && !strcmp(e, "warp")) ? 0 : 1;
+    e = getenv("THR_BM25_UNITS_PER_SM");
+    // warp kernel, measured: 1 beats 2..5 at 1.25M and 10M docs (fewer threshold warm-ups)
+    units_per_cta = e ? atoi(e) : (impl_span ? kSpanUnitsPerCta : 1);
+    if (units_per_cta < 1) units_per_cta = 1;
+    e = getenv("THR_BM25_RANGE_COST");
+    range_cost = e ? atoll(e) : (long long)(impl_span ? kSpanRangeCost : kRangeCostDefault);
   }
-  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, h->num_sms * units_per_sm, (unsigned long long)range_cost, units,
+  const int grid = impl_span ? kSpanCtas * h->num_sms : h->num_sms;
+  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, grid * units_per_cta, (unsigned long long)range_cost, units,
                                       unit_base, total_units, counter);
   THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
   bm25_order_kernel<<<32, 256, 0, s>>>(units, total_units, order);
@@ -762,11 +1154,20 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.units = units; a.total_units = total_units;
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.status = h->d_status;
-  THR_CUDA(h, cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBm25Smem));
-  tok = thr_prof_begin(h, THR_PROF_BM25, s);
-  bm25_kernel<<<h->num_sms, kThreads, kBm25Smem, s>>>(a);
-  thr_prof_end(h, tok, s);
-  THR_CHECK_LAUNCH(h, "bm25_kernel");
+  if (impl_span) {
+    THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmem));
+    THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    tok = thr_prof_begin(h, THR_PROF_BM25, s);
+    bm25_span_kernel<<<grid, kSpanThreads + 32, kSpanSmem, s>>>(a);
+    thr_prof_end(h, tok, s);
+    THR_CHECK_LAUNCH(h, "bm25_span_kernel");
+  } else {
+    THR_CUDA(h, cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBm25Smem));
+    tok = thr_prof_begin(h, THR_PROF_BM25, s);
+    bm25_kernel<<<grid, kThreads, kBm25Smem, s>>>(a);
+    thr_prof_end(h, tok, s);
+    THR_CHECK_LAUNCH(h, "bm25_kernel");
+  }
   tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   size_t merge_slots = 32;
   while (merge_slots < (size_t)kMaxUnitsPerQuery * k) merge_slots <<= 1;
