@@ -572,8 +572,11 @@ constexpr int kSpanCtas = THR_SPAN_CTAS;          // CTAs per SM
 constexpr int kSpanBar = 1;                       // named barrier of the consumers
 constexpr int kPerThread = kChunk / kSpanThreads; // postings per consumer thread and chunk
 constexpr int kScanIters = kSpanDocs / (4 * kSpanThreads);
-constexpr int kIssue = kStages / 2 < 1 ? 1 : kStages / 2;   // chunks the producer issues per round (half the ring)
-constexpr int kScanBatch = kScanIters < 8 ? kScanIters : 8;
+#ifndef THR_SPAN_ISSUE
+#define THR_SPAN_ISSUE (THR_SPAN_STAGES / 2)
+#endif
+constexpr int kIssue = THR_SPAN_ISSUE;   // chunks the producer issues per round (half the ring)
+constexpr int kScanBatch = kScanIters % 8 == 0 ? 8 : kScanIters % 6 == 0 ? 6 : kScanIters % 4 == 0 ? 4 : 1;
 static_assert(kScanIters % kScanBatch == 0, "scan batches");
 static_assert(kChunk % kSpanThreads == 0 && kChunk % 2 == 0 && kPerThread >= 1 && kPerThread <= 8, "chunk shape");
 static_assert(kSpanDocs % kMaxBlkDocs == 0 && kSpanDocs % (4 * kSpanThreads) == 0, "span shape");
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
               if (j == total - 1) fl |= kFEndSpan;
               uint32_t st = s + (uint32_t)lane, php = ph;
               if (st >= (uint32_t)kStages) { st -= kStages; php ^= 1u; }
-              mbar_wait_relaxed(empty_u + st * 8u, php ^ 1u, a.status, 472);
+              mbar_wait(empty_u + st * 8u, php ^ 1u, a.status, 472);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + st * 16u),
                            "r"((uint32_t)m | ((uint32_t)slack << 16) | (fl << 24)), "r"(w_t), "r"(doc0), "r"((uint32_t)unit)
                            : "memory");
@@ -761,17 +764,19 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
     bar_group<kSpanThreads, kSpanBar>();
   };
   for (;;) {
-    mbar_wait(full_u + s * 8u, ph, a.status, 471);
+    // Every consumer warp passes here once per chunk, most of them without a posting of their own (a chunk holds
+    // a few hundred postings on average): the common path is kept to the poll, the descriptor, the term barrier
+    // and the release.
+    if (!mbar_try_wait(full_u + s * 8u, ph)) mbar_wait(full_u + s * 8u, ph, a.status, 471);
     uint32_t dx, dy, dz, dw;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dx), "=r"(dy), "=r"(dz), "=r"(dw) : "r"(desc_u + s * 16u));
     const uint32_t fl = dx >> 24;
     const int count = (int)(dx & 0xffffu);
-    if (fl & kFNewUnit) { unit = (int)dw; tau = 0.f; }
     if (fl & kFSync) bar_group<kSpanThreads, kSpanBar>();     // the previous term's adds are complete
 #ifdef THR_ABL_NOADD
     if (false) {
 #else
-    if (count > 0) {
+    if (tid < count) {
 #endif
       const float w = __uint_as_float(dy);
       const uint32_t acc0 = acc_u - dz * 4u;                  // &acc[doc - doc0] == acc0 + doc * 4
@@ -781,22 +786,24 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
 #pragma unroll
       for (int u = 0; u < kPerThread; ++u) {
         d[u] = 0; im[u] = 0.f;
-        if (tid + u * kSpanThreads < count)
+        if (u == 0 || tid + u * kSpanThreads < count)
           asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(d[u]), "=f"(im[u]) : "r"(pa + (uint32_t)u * (kSpanThreads * 8u)));
       }
 #pragma unroll
       for (int u = 0; u < kPerThread; ++u) {
         o[u] = 0.f;
-        if (tid + u * kSpanThreads < count) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o[u]) : "r"(acc0 + d[u] * 4u));
+        if (u == 0 || tid + u * kSpanThreads < count) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o[u]) : "r"(acc0 + d[u] * 4u));
       }
 #pragma unroll
       for (int u = 0; u < kPerThread; ++u)
-        if (tid + u * kSpanThreads < count)
+        if (u == 0 || tid + u * kSpanThreads < count)
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc0 + d[u] * 4u), "f"(__fadd_rn(o[u], __fmul_rn(w, im[u]))) : "memory");
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_u + s * 8u);
     if (++s == kStages) { s = 0; ph ^= 1u; }
+    if (!(fl & (kFNewUnit | kFEndSpan | kFEndUnit | kFExit))) continue;
+    if (fl & kFNewUnit) { unit = (int)dw; tau = 0.f; }
 
 #ifdef THR_ABL_NOSCAN
     if (false) {
