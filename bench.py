@@ -385,10 +385,10 @@ def main():
                      "hbm_gbs": x_bytes / (dense_avg * 1e-3) / 1e9 if dense_avg > 0 else 0.0,
                      "hbm_frac": (x_bytes / (dense_avg * 1e-3) / 1e9) / hbm if dense_avg > 0 else None,
                      "launch_ms": dense_avg, "launches": dense_n},
-        "bm25_roofline": {"kernel": "bm25_kernel", "bound": "hbm", "algorithmic_bytes": bm25_bytes,
+        "bm25_roofline": {"kernel": "bm25_span_kernel", "bound": "hbm", "algorithmic_bytes": bm25_bytes,
                           "achieved": bm25_bytes / (bm25_ms * 1e-3) / 1e9 if bm25_ms > 0 else 0.0, "peak": hbm,
                           "unit": "GB/s", "frac": (bm25_bytes / (bm25_ms * 1e-3) / 1e9) / hbm if bm25_ms > 0 else None,
-                          "traffic": traffic.get("bm25_kernel", {}).get("dram_bytes_per_launch")},
+                          "traffic": traffic.get("bm25_span_kernel", {}).get("dram_bytes_per_launch")},
         "setup_s": round(setup_s, 1),
     }
     if world == 1 and not args.no_cpu_baseline:

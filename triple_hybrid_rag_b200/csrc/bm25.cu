@@ -11,39 +11,20 @@
 // Index (include/thr.h): postings {u32 doc, f32 impact} in term-major CSR order (doc ascending inside
 // a term) and skip[t * n_blk + r] = first posting of term t whose doc lies in range r (blk_docs docs).
 //
-// One CTA works on one unit (a query restricted to a span of doc ranges; heavy queries are cut into
-// several units) at a time.  The kernel is issue-bound, not DRAM-bound (a query touches ~13% of the docs, so
-// a range of 2048 docs carries only a few hundred postings): what matters is the number of instructions
-// per posting.  Therefore every warp is autonomous: it OWNS whole ranges — a contiguous run of the unit's
-// ranges, with a private 2048-slot fp32 accumulator in shared memory — and does everything for them:
-//   * reads the terms' skip entries (lane t <-> query term t, loaded two ranges ahead),
-//   * pulls the terms' posting segments of the NEXT range into its own double-buffered staging area in
-//     shared memory with cp.async.bulk (one copy per term, issued by the term's lane, completion on a
-//     per-warp mbarrier) and hints the range after that into L2, so DRAM latency overlaps the current
-//     range's arithmetic (segments that do not fit the 272-posting buffer are read from global),
-//   * accumulates term by term in query order (__syncwarp between terms: no atomics, no block barriers),
-//   * re-walks the postings, takes each touched doc's final score once, re-zeroes the slot and appends the
-//     score to the CTA's candidate list if it beats the running threshold tau.
-// The 16 warps of a CTA only meet at round boundaries (a round = 1..8 ranges per warp): there the
-// candidate list is compacted to the best k by a radix select when it is half full (which raises tau).
-// An append that would overflow the list raises a flag instead; the round is then rolled back and redone
-// serially with compactions in between (cannot overflow: one range appends at most 2048 <= cap - k).
+// Launch sequence of thr_bm25_topk: cost per query -> plan (cut queries into units = doc-range slices of
+// about equal cost) -> order (heaviest first) -> bm25_span_kernel (one unit at a time per CTA, fetched
+// dynamically; writes each unit's sorted top-k) -> bm25_merge_kernel (per query, merge its units' lists).
+// The kernel is bound by instruction issue and latency, not by DRAM: a query touches ~13% of the docs, so
+// what counts is the number of (term, span) visits and the instructions each visit costs.
 #include <math_constants.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kMaxTerms = 32;
-constexpr int kWarps = 16;
-constexpr int kThreads = kWarps * 32;            // 512
-constexpr int kConsumers = kThreads;
-constexpr int kMaxBlkDocs = 2048;                // docs per range = accumulator slots per warp
-constexpr int kMaxSelB = 256;
-constexpr int kCandCap = 2560;                   // >= kMaxBlkDocs + 2 * kMaxSelB
-constexpr int kStage = 272;                      // postings per warp staging buffer (two per warp)
-constexpr int kSmallSeg = 48;                    // segments up to this many postings are staged first
-constexpr int kMaxRound = 32;                    // ranges per warp and round, at most
+constexpr int kMaxTerms = 32;                    // lanes of the producer warp: one per query term
+constexpr int kMaxBlkDocs = 2048;                // largest skip range
+constexpr int kMaxSelB = 256;                    // largest k
 
 struct Posting { uint32_t doc; float imp; };
 
@@ -68,14 +49,6 @@ struct Bm25Args {
   int32_t* part_cnt;      // [max_units]
   thr_dev_status* status;
 };
-
-__device__ __forceinline__ void bar_consumers() { __syncthreads(); }
-
-__device__ __forceinline__ uint2 ldg_posting(const Posting* p) {
-  uint2 v;
-  asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-}
 
 // Pull [p, p + bytes) into L2 (16-byte granules); no destination, no completion to wait for.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
@@ -147,391 +120,8 @@ __device__ uint64_t block_compact_topk_t(uint64_t* keys, int n, int ksel, uint32
   bar_group<kNT, kBar>();
   return T;
 }
-__device__ __forceinline__ uint64_t block_compact_topk(uint64_t* keys, int n, int ksel, uint32_t* hist,
-                                                       unsigned long long* s_prefix, int* s_want, int* s_cnt, int tid) {
-  return block_compact_topk_t<kConsumers, kCandCap, 0>(keys, n, ksel, hist, s_prefix, s_want, s_cnt, tid);
-}
-
-constexpr size_t kSmemAcc = (size_t)kWarps * kMaxBlkDocs * 4;
-constexpr size_t kSmemCand = (size_t)kCandCap * 8;
-constexpr size_t kSmemStage = (size_t)kWarps * 2 * kStage * sizeof(Posting);
-constexpr size_t kSmemMisc = 256 * 4 + kMaxTerms * 8 + 8 + 8 * 4 + kWarps * 2 * 8;
-constexpr size_t kBm25Smem = kSmemAcc + kSmemCand + kSmemStage + kSmemMisc + 256;
-static_assert(kBm25Smem <= 232448, "shared memory budget of one SM");
-
-__global__ void __launch_bounds__(kThreads, 1) bm25_kernel(const Bm25Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* acc = (float*)gen;                                                    // [kWarps][kMaxBlkDocs]
-  uint64_t* cand = (uint64_t*)(acc + kWarps * kMaxBlkDocs);                    // kCandCap
-  Posting* stage = (Posting*)(cand + kCandCap);                               // [kWarps][2][kStage]
-  uint64_t* sbar = (uint64_t*)(stage + kWarps * 2 * kStage);                  // [kWarps][2] mbarriers
-  uint32_t* hist = (uint32_t*)(sbar + kWarps * 2);                            // 256
-  int* q_term = (int*)(hist + 256);                                           // kMaxTerms
-  float* q_idf = (float*)(q_term + kMaxTerms);                                // kMaxTerms
-  unsigned long long* s_prefix = (unsigned long long*)(q_idf + kMaxTerms);
-  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=unit [4]=nterms [5]=overflow [6]=bound
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < kWarps * kMaxBlkDocs; i += kThreads) acc[i] = 0.f;
-  if (lane == 0) {
-    mbar_init(smem_u32(&sbar[warp * 2]), 1);
-    mbar_init(smem_u32(&sbar[warp * 2 + 1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const uint32_t stage_w = smem_u32(stage + (size_t)warp * 2 * kStage);       // this warp's two staging buffers
-  const uint32_t sbar_w = smem_u32(&sbar[warp * 2]);
-  uint32_t seq = 0;   // staged ranges so far (per warp, across units): buffer = seq & 1, parity = (seq >> 1) & 1
-  const uint32_t accw = smem_u32(acc) + (uint32_t)warp * kMaxBlkDocs * 4u;   // this warp's accumulator
-  volatile int* v_cnt = &s_int[2];
-  volatile int* v_ovf = &s_int[5];
-
-  for (;;) {
-    // ---- fetch the next unit (whole CTA) ----
-    __syncthreads();
-    if (tid == 0) {
-      int w = atomicAdd(a.work_counter, 1);
-      s_int[3] = w < *a.total_units ? a.order[w] : -1;
-    }
-    __syncthreads();
-    const int unit = s_int[3];
-    if (unit < 0) break;
-    const int q = a.units[unit].q;
-    const int r_begin = a.units[unit].r0, r_end = a.units[unit].r1;
-    if (tid < kMaxTerms) {
-      const int lo = a.q_off[q], hi = a.q_off[q + 1];
-      int nt = hi - lo;
-      if (nt > kMaxTerms) nt = kMaxTerms;  // host rejects longer queries; keep the kernel safe
-      int t = -1;
-      float w = 0.f;
-      if (tid < nt) {
-        t = a.q_terms[lo + tid];
-        if (t < 0 || t >= a.V) t = -1; else w = a.idf[t];
-      }
-      q_term[tid] = t;
-      q_idf[tid] = w;
-      if (tid == 0) { s_int[4] = nt; s_int[2] = 0; s_int[5] = 0; }
-    }
-    __syncthreads();
-    const int nterms = s_int[4];
-
-    // this warp's contiguous run of ranges
-    const int n_ranges = r_end - r_begin;
-    const int per_warp = (n_ranges + kWarps - 1) / kWarps;        // same for every warp: the round loop is uniform
-    const int my_r0 = min(r_end, r_begin + warp * per_warp);
-    const int my_n = min(r_end, my_r0 + per_warp) - my_r0;
-    const int my_term = lane < nterms ? q_term[lane] : -1;
-    const float my_w = lane < nterms ? q_idf[lane] : 0.f;
-    const int64_t* row = a.skip + (size_t)(my_term < 0 ? 0 : my_term) * a.n_blk;  // lane t <-> query term t
-    float tau = 0.f;  // only score > 0 is eligible; raised by compactions
-
-    // rare path: one candidate per calling lane; an append that does not fit raises the overflow flag
-    auto emit1 = [&](float v, uint32_t doc) {
-      const int pos = atomicAdd(&s_int[2], 1);
-      if (pos < kCandCap) cand[pos] = pack_key(v, doc);
-      else *v_ovf = 1;
-    };
-    auto compact = [&]() {
-      const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-      // One ulp below the k-th best score: warps walk their runs concurrently, so a doc that TIES with the
-      // k-th best can still arrive later with a smaller id and must pass the strict "> tau" filter.
-      tau = f32_from_orderable((uint32_t)(T >> 32) - 1u);
-      if (tid == 0) s_int[2] = s_int[1];
-      bar_consumers();
-    };
-    // accumulate / extract one posting (shared-space addressing)
-    auto rmw = [&](uint32_t acc0, uint32_t doc, float contrib) {
-      const uint32_t aa = acc0 + doc * 4u;
-      float old;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old) : "r"(aa));
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(__fadd_rn(old, contrib)) : "memory");
-    };
-    auto take = [&](uint32_t acc0, uint32_t doc) {
-      const uint32_t aa = acc0 + doc * 4u;
-      float v;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(aa));
-      if (v != 0.f) {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(0.f) : "memory");
-        if (v > tau) emit1(v, doc);
-      }
-    };
-    // One range, no prefetch state (serial redo path and term slots >= kFast): everything from global.
-    float best_v = 0.f;        // sampling mode: this lane's best (score, doc) of the range
-    uint32_t best_doc = 0;
-    auto slots_from_global = [&](int r, int g_begin, uint32_t acc0, int64_t p_lo, int64_t p_hi, int mode) {
-      const int cnt = my_term >= 0 ? (int)(p_hi - p_lo) : 0;
-      unsigned live = __ballot_sync(0xffffffffu, cnt > 0) & ~((1u << g_begin) - 1u);
-      for (unsigned rem = live; rem; rem &= rem - 1) {
-        const int g = __ffs(rem) - 1;
-        const int n = __shfl_sync(0xffffffffu, cnt, g);
-        const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p_lo, g);
-        const float w = __shfl_sync(0xffffffffu, my_w, g);
-        for (int i = lane; i < n; i += 32) {
-          const uint2 p = ldg_posting(seg + i);
-          if (mode == 0) rmw(acc0, p.x, __fmul_rn(w, __uint_as_float(p.y)));
-          else if (mode == 1) take(acc0, p.x);
-          else {  // sample: zero the slot, remember this lane's best
-            const uint32_t aa = acc0 + p.x * 4u;
-            float v;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(aa));
-            if (v != 0.f) {
-              asm volatile("st.shared.f32 [%0], %1;" ::"r"(aa), "f"(0.f) : "memory");
-              if (v > best_v) { best_v = v; best_doc = p.x; }
-            }
-          }
-        }
-        __syncwarp();  // the same doc may recur in the next term
-      }
-      (void)r;
-    };
-
-    // ---- prologue of the per-warp pipeline: skip entries of the first ranges ----
-    int64_t p0 = 0, p1 = 0, p2 = 0;          // skip[r], skip[r + 1], skip[r + 2] of this lane's term
-    if (my_n > 0 && my_term >= 0) {
-      p0 = __ldg(row + my_r0);
-      p1 = __ldg(row + my_r0 + 1);
-      p2 = my_n > 1 ? __ldg(row + my_r0 + 2) : p1;
-    }
-    // Stage the postings [lo_l, hi_l) of every term (lane) into buffer (seq_no & 1).  Returns, packed, this
-    // lane's first staged posting and how many of its postings are staged (the rest is read from global).
-    auto stage_issue = [&](int64_t lo_l, int64_t hi_l, uint32_t seq_no) -> int {
-      const int cnt = my_term >= 0 ? (int)(hi_l - lo_l) : 0;
-      const int slack = (int)(lo_l & 1);                       // copies start at an even posting (16-byte granules)
-      const int cp = cnt > 0 ? ((slack + cnt + 1) & ~1) : 0;   // postings copied
-      // Small segments first (they are most of the visits and the worst case for a global read), then the
-      // large ones in term order while room remains; each class is packed by a warp scan.
-      const bool small_seg = cnt > 0 && cp <= kSmallSeg;
-      int incl_s = small_seg ? cp : 0, incl_b = (cnt > 0 && !small_seg) ? cp : 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int vs = __shfl_up_sync(0xffffffffu, incl_s, d);
-        const int vb = __shfl_up_sync(0xffffffffu, incl_b, d);
-        if (lane >= d) { incl_s += vs; incl_b += vb; }
-      }
-      const bool fits_s = small_seg && incl_s <= kStage;
-      const int used_s = (int)__reduce_max_sync(0xffffffffu, (unsigned)(fits_s ? incl_s : 0));
-      const bool big = cnt > 0 && !small_seg;
-      const int slot0 = fits_s ? incl_s - cp : used_s + incl_b - cp;   // first buffer entry of this lane's copy
-      int st_cp = 0;                                                    // postings copied into the buffer
-      if (fits_s) st_cp = cp;
-      else if (big && slot0 + cp <= kStage) st_cp = cp;
-      else if (big && slot0 + 64 <= kStage) st_cp = (kStage - slot0) & ~1;   // the first one that does not fit: a prefix
-      const int bytes = (int)__reduce_add_sync(0xffffffffu, (unsigned)st_cp) * 8;
-      const uint32_t bar = sbar_w + (seq_no & 1u) * 8u;
-      fence_proxy_async_smem();   // this warp's earlier reads of the buffer precede the async writes
-      if (lane == 0) {
-        if (bytes > 0) mbar_arrive_expect_tx(bar, (uint32_t)bytes);
-        else mbar_arrive(bar);
-      }
-      __syncwarp();
-      if (st_cp > 0) {
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            :
-            : "r"(stage_w + ((seq_no & 1u) * kStage + (uint32_t)slot0) * 8u), "l"(a.post + (lo_l - slack)),
-              "r"((uint32_t)st_cp * 8u), "r"(bar)
-            : "memory");
-      }
-      // (first staged posting) | (number of staged postings) << 16
-      const int st_n = st_cp == cp ? cnt : max(0, st_cp - slack);
-      return (slot0 + slack) | (st_n << 16);
-    };
-    int cur_off = 0, nxt_off = 0;
-    if (my_n > 0) cur_off = stage_issue(p0, p1, seq);
-
-    // ---- round 0: a threshold to start from.  Every warp scores its first range and contributes only
-    // each lane's best doc (<= 512 samples per CTA); the k-th best sample, one ulp lower, is a valid lower
-    // bound of the unit's k-th best score.  The samples are then dropped: the ranges are scored again
-    // below, now without the flood of appends a zero threshold would cause.
-    if (my_n > 0) {
-      const uint32_t acc0 = accw - ((uint32_t)my_r0 << a.blk_shift) * 4u;
-      slots_from_global(my_r0, 0, acc0, p0, p1, 0);
-      slots_from_global(my_r0, 0, acc0, p0, p1, 2);
-      if (best_v > 0.f) emit1(best_v, best_doc);
-    }
-    __syncthreads();
-    if (*v_cnt > a.k) {
-      const uint64_t T = block_compact_topk(cand, *v_cnt, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-      tau = f32_from_orderable((uint32_t)(T >> 32) - 1u);
-    }
-    __syncthreads();
-    if (tid == 0) s_int[2] = 0;
-    __syncthreads();
-
-    // ---- rounds ----
-    int done = 0;       // ranges of this warp's run already processed (same value in every warp)
-    int per_round = 1;
-    while (done < per_warp) {
-      const int cnt_round_start = *v_cnt;   // stable: every warp is between two round barriers
-      const int todo = min(per_round, per_warp - done);
-      for (int jj = 0; jj < todo; ++jj) {
-        const int j = done + jj;
-        if (j >= my_n) break;
-        const int r = my_r0 + j;
-        const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;  // &acc_w[doc - doc0] == acc0 + doc*4
-        // skip entry three ranges ahead (used at the end of this range), next range's postings -> staging
-        int64_t p3 = p2;
-        if (my_term >= 0 && j + 3 <= my_n) p3 = __ldg(row + r + 3);
-        if (j + 1 < my_n) nxt_off = stage_issue(p1, p2, seq + 1);
-        const int cnt = my_term >= 0 ? (int)(p1 - p0) : 0;
-        const unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
-        // this range's staged postings have landed?
-        mbar_wait(sbar_w + (seq & 1u) * 8u, (seq >> 1) & 1u, a.status, 450);
-        const uint32_t sbuf = stage_w + (seq & 1u) * kStage * 8u;
-        ++seq;
-        // One walk over the range's postings, term by term: the staged part of a segment from shared memory,
-        // the rest (what did not fit the staging buffer) from global with four chunks in flight.
-        auto walk = [&](const bool extract) {
-          for (unsigned rem = live; rem; rem &= rem - 1) {
-            const int g = __ffs(rem) - 1;
-            const int n = __shfl_sync(0xffffffffu, cnt, g);
-            const int so = __shfl_sync(0xffffffffu, cur_off, g);
-            const float w = __shfl_sync(0xffffffffu, my_w, g);
-            const int st_n = so >> 16;
-            const uint32_t first = sbuf + (uint32_t)(so & 0xffff) * 8u;
-            const uint32_t end = first + (uint32_t)st_n * 8u;
-            for (uint32_t pa = first + lane * 8u; pa < end; pa += 256u) {
-              uint32_t doc;
-              float imp;
-              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(doc), "=f"(imp) : "r"(pa));
-              if (extract) take(acc0, doc); else rmw(acc0, doc, __fmul_rn(w, imp));
-            }
-            if (st_n < n) {
-              const Posting* seg = a.post + __shfl_sync(0xffffffffu, (long long)p0, g) + st_n;
-              const int m = n - st_n;
-              for (int i = lane; i < m; i += 128) {
-                uint2 pp[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (i + 32 * u < m) pp[u] = ldg_posting(seg + i + 32 * u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (i + 32 * u < m) {
-                    if (extract) take(acc0, pp[u].x); else rmw(acc0, pp[u].x, __fmul_rn(w, __uint_as_float(pp[u].y)));
-                  }
-              }
-            }
-            __syncwarp();  // the same doc may recur in the next term
-          }
-        };
-        if (live) {
-          walk(false);   // pass 1: accumulate in term order
-          walk(true);    // pass 2: first visit of a doc takes its final score and zeroes the slot
-        }
-        // this term's postings three ranges ahead -> L2 (the staging copy then hits L2, not DRAM)
-        if (p3 > p2) {
-          const int64_t b = p2 & ~(int64_t)1;
-          prefetch_l2_bulk(a.post + b, (uint32_t)(((p3 - b) * 8 + 15) & ~(int64_t)15));
-        }
-        // rotate the pipeline
-        p0 = p1; p1 = p2; p2 = p3;
-        cur_off = nxt_off;
-      }
-
-      // ---- round barrier: overflow roll-back, compaction, size of the next round ----
-      __syncthreads();
-      const int cnt_round_end = *v_cnt;      // stable until the next barrier (may exceed the capacity after an overflow)
-      const bool overflowed = *v_ovf != 0;
-      __syncthreads();
-      if (overflowed) {
-        // Discard this round's appends and redo its ranges in sub-rounds of ONE range per warp, all warps
-        // in parallel from global memory (the accumulators are zero again: pass 2 zeroes even when an append
-        // is dropped).  Before each sub-round the warps add up how many docs they can append at most; if that
-        // does not fit even after a compaction, the sub-round runs one warp at a time (a single range
-        // appends at most 2048 <= capacity - k).
-        if (tid == 0) { s_int[2] = cnt_round_start; s_int[5] = 0; }
-        __syncthreads();
-        for (int jj = 0; jj < todo; ++jj) {
-          const int j = done + jj;
-          const bool mine = j < my_n;
-          const int r = my_r0 + j;
-          const uint32_t acc0 = accw - ((uint32_t)r << a.blk_shift) * 4u;
-          int64_t lo_l = 0, hi_l = 0;
-          if (mine && my_term >= 0) { lo_l = __ldg(row + r); hi_l = __ldg(row + r + 1); }
-          int touched = (int)(hi_l - lo_l);
-#pragma unroll
-          for (int sft = 16; sft > 0; sft >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, sft);
-          touched = min(touched, a.blk_docs);
-          if (tid == 0) s_int[6] = 0;
-          __syncthreads();
-          if (lane == 0) atomicAdd(&s_int[6], touched);
-          __syncthreads();
-          const int bound = s_int[6];
-          int cnt_now = *v_cnt;
-          __syncthreads();                       // everyone has read the counters before anyone changes them
-          if (cnt_now + bound > kCandCap && cnt_now > a.k) {
-            compact();
-            cnt_now = *v_cnt;
-            __syncthreads();
-          }
-          if (cnt_now + bound <= kCandCap) {
-            if (mine) {
-              slots_from_global(r, 0, acc0, lo_l, hi_l, 0);
-              slots_from_global(r, 0, acc0, lo_l, hi_l, 1);
-            }
-            __syncthreads();
-          } else {
-            for (int wsel = 0; wsel < kWarps; ++wsel) {
-              const bool need = *v_cnt + kMaxBlkDocs > kCandCap;  // stable here; true implies count > k
-              __syncthreads();
-              if (need) compact();
-              if (warp == wsel && mine) {
-                slots_from_global(r, 0, acc0, lo_l, hi_l, 0);
-                slots_from_global(r, 0, acc0, lo_l, hi_l, 1);
-              }
-              __syncthreads();
-            }
-          }
-        }
-        if (*v_ovf) dev_report(a.status, THR_EOVERFLOW, 440, *v_cnt);  // excluded by construction
-        __syncthreads();
-      }
-      // uniform after the barrier; early rounds compact sooner: a good threshold early saves appends later
-      if (*v_cnt > (per_round <= 4 ? max(2 * a.k, 256) : kCandCap / 2)) compact();
-      done += todo;
-      // Next round: twice as long, but no longer than what the appends of this round (per range and warp)
-      // predict to fill half of the free candidate slots — an overflow costs a whole redo.
-      {
-        const int appended = max(overflowed ? kCandCap : cnt_round_end - cnt_round_start, 1);
-        const int room = max(kCandCap - *v_cnt, 0) / 2;
-        const long long fit = (long long)room * todo / appended;
-        per_round = (int)max(1ll, min((long long)min(2 * per_round, kMaxRound), fit));
-      }
-      __syncthreads();
-    }
-
-    // ---- end of unit: final top-k, sorted ----
-    int n = *v_cnt;
-    if (n > a.k) {
-      (void)block_compact_topk(cand, n, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-      n = s_int[1];
-      bar_consumers();
-    }
-    // bitonic sort (descending) of <= 256 keys padded with 0
-    for (int i = n + tid; i < kMaxSelB; i += kConsumers) cand[i] = 0ull;
-    bar_consumers();
-    for (int size = 2; size <= kMaxSelB; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        if (tid < kMaxSelB / 2) {
-          int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
-          int hi = lo + stride;
-          bool desc_block = ((lo & size) == 0);
-          uint64_t x = cand[lo], y = cand[hi];
-          bool swap = desc_block ? (y > x) : (x > y);
-          if (swap) { cand[lo] = y; cand[hi] = x; }
-        }
-        bar_consumers();
-      }
-    }
-    if (tid == 0) a.part_cnt[unit] = n;
-    for (int i = tid; i < n; i += kConsumers) a.part_keys[(size_t)unit * a.k + i] = cand[i];
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Span kernel: the CTA, not the warp, owns the accumulator.
+// The CTA owns the accumulator.
 //
 // A span is kSpanDocs consecutive docs (a whole number of skip ranges) with one fp32 accumulator slot per doc
 // in shared memory.  A term's postings inside a span are ONE contiguous piece of the term-major posting array
@@ -626,11 +216,7 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
       if (lane == 0) {
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + s * 16u), "r"(x), "r"(y), "r"(z), "r"(w)
                      : "memory");
-#ifdef THR_ABL_NOCOPY
-        if (false) {
-#else
         if (bytes) {
-#endif
           mbar_arrive_expect_tx(full_u + s * 8u, bytes);
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -671,12 +257,7 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
       for (int sp = 0; sp < nsp; ++sp) {
         const int64_t e4 = edge(sp + 4);
         // the span after the next one -> L2 (the ring then pulls from L2, not DRAM); capped per term
-#ifndef THR_ABL_NOPF
-        if (e3 > e2)
-#else
-        if (false)
-#endif
-        {
+        if (e3 > e2) {
           const int64_t b = e2 & ~(int64_t)1;
           const int64_t nby = min((e3 - b) * 8, (int64_t)32768);
           prefetch_l2_bulk(a.post + b, (uint32_t)((nby + 15) & ~(int64_t)15));
@@ -773,11 +354,7 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
     const uint32_t fl = dx >> 24;
     const int count = (int)(dx & 0xffffu);
     if (fl & kFSync) bar_group<kSpanThreads, kSpanBar>();     // the previous term's adds are complete
-#ifdef THR_ABL_NOADD
-    if (false) {
-#else
     if (tid < count) {
-#endif
       const float w = __uint_as_float(dy);
       const uint32_t acc0 = acc_u - dz * 4u;                  // &acc[doc - doc0] == acc0 + doc * 4
       const uint32_t pa = ring_u + s * (uint32_t)(kChunk * 8) + (((dx >> 16) & 1u) + (uint32_t)tid) * 8u;
@@ -805,11 +382,7 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
     if (!(fl & (kFNewUnit | kFEndSpan | kFEndUnit | kFExit))) continue;
     if (fl & kFNewUnit) { unit = (int)dw; tau = 0.f; }
 
-#ifdef THR_ABL_NOSCAN
-    if (false) {
-#else
     if (fl & kFEndSpan) {
-#endif
       bar_group<kSpanThreads, kSpanBar>();                    // every add of the span has landed
       for (;;) {
         const uint32_t sa = acc_u + (uint32_t)tid * 16u;
@@ -922,8 +495,7 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
 // per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
-constexpr unsigned long long kRangeCostDefault = 96;
-constexpr unsigned long long kSpanRangeCost = 200;   // span kernel: the scan of a range is worth about this many postings
+constexpr unsigned long long kSpanRangeCost = 200;   // the scan of a range is worth about this many postings
 constexpr int kSpanUnitsPerCta = 2;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_slots, unsigned long long kRangeCost,
@@ -1133,21 +705,17 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys, h->d_status);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
-  // Which kernel: the span kernel (CTA-owned accumulator, 2 CTAs per SM) unless THR_BM25_IMPL=warp asks for the
-  // warp-autonomous one.  Work is cut into about `slots` units of equal cost (heaviest first, fetched dynamically).
-  static int impl_span = -1, units_per_cta = 0;
+  // Work is cut into about `grid * units_per_cta` units of equal cost (heaviest first, fetched dynamically).
+  static int units_per_cta = 0;
   static long long range_cost = -1;
-  if (impl_span < 0) {
-    const char* e = getenv("THR_BM25_IMPL");
-    impl_span = (e && !strcmp(e, "warp")) ? 0 : 1;
-    e = getenv("THR_BM25_UNITS_PER_SM");
-    // warp kernel, measured: 1 beats 2..5 at 1.25M and 10M docs (fewer threshold warm-ups)
-    units_per_cta = e ? atoi(e) : (impl_span ? kSpanUnitsPerCta : 1);
+  if (!units_per_cta) {
+    const char* e = getenv("THR_BM25_UNITS_PER_SM");   // measured flat between 1 and 4 at 10M docs
+    units_per_cta = e ? atoi(e) : kSpanUnitsPerCta;
     if (units_per_cta < 1) units_per_cta = 1;
     e = getenv("THR_BM25_RANGE_COST");
-    range_cost = e ? atoll(e) : (long long)(impl_span ? kSpanRangeCost : kRangeCostDefault);
+    range_cost = e ? atoll(e) : (long long)kSpanRangeCost;
   }
-  const int grid = impl_span ? kSpanCtas * h->num_sms : h->num_sms;
+  const int grid = kSpanCtas * h->num_sms;
   bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, grid * units_per_cta, (unsigned long long)range_cost, units,
                                       unit_base, total_units, counter);
   THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
@@ -1161,20 +729,12 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.units = units; a.total_units = total_units;
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.status = h->d_status;
-  if (impl_span) {
-    THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmem));
-    THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    tok = thr_prof_begin(h, THR_PROF_BM25, s);
-    bm25_span_kernel<<<grid, kSpanThreads + 32, kSpanSmem, s>>>(a);
-    thr_prof_end(h, tok, s);
-    THR_CHECK_LAUNCH(h, "bm25_span_kernel");
-  } else {
-    THR_CUDA(h, cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBm25Smem));
-    tok = thr_prof_begin(h, THR_PROF_BM25, s);
-    bm25_kernel<<<grid, kThreads, kBm25Smem, s>>>(a);
-    thr_prof_end(h, tok, s);
-    THR_CHECK_LAUNCH(h, "bm25_kernel");
-  }
+  THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmem));
+  THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  tok = thr_prof_begin(h, THR_PROF_BM25, s);
+  bm25_span_kernel<<<grid, kSpanThreads + 32, kSpanSmem, s>>>(a);
+  thr_prof_end(h, tok, s);
+  THR_CHECK_LAUNCH(h, "bm25_span_kernel");
   tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   size_t merge_slots = 32;
   while (merge_slots < (size_t)kMaxUnitsPerQuery * k) merge_slots <<= 1;
