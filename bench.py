@@ -111,6 +111,9 @@ class ClockSampler:
                 "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "NVML getters every 20 ms"}
 
 
+RUN_AHEAD = int(os.environ.get("THR_BENCH_RUN_AHEAD", "3"))
+
+
 def make_config(args, world: int):
     N, D, B, k, V = args.chunks, args.dim, args.batch, args.k, args.vocab
     return {"workload": f"triple-hybrid top-{k}: dense {N}x{D} bf16 + BM25 {N} docs V={V} (Zipf) + weighted RRF "
@@ -270,12 +273,26 @@ def main():
     # and lazily loaded kernels are in their steady state before the timed region (short steps — small shards —
     # otherwise start timing while the GPU is still ramping up from idle clocks).
     def run_steps(n):
-        for _ in range(n):
-            searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+        # Same allocation pattern as the timed loop (the previous step's outputs stay alive while the next step
+        # allocates): otherwise the caching allocator meets a new high-water mark in the SECOND timed step and
+        # calls cudaMalloc there, which synchronises the device and, with peer access enabled (N > 1), takes
+        # 40-80 ms on every rank at once.
+        evs, keep = [], None
+        for i in range(n):
+            keep = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+            e = torch.cuda.Event()
+            e.record()
+            evs.append(e)
+            if i >= RUN_AHEAD:  # same bounded run-ahead as the timed loop
+                evs[i - RUN_AHEAD].synchronize()
         eng.sync()
 
     n_warm = max(args.warmup, 3)
+    # The barrier's own collective (an all-reduce) is part of the warm-up too (NCCL connects a collective's
+    # channels lazily at its first use).
+    barrier()
     run_steps(n_warm)
+    barrier()
     t_w = time.perf_counter()
     run_steps(3)
     extra = torch.tensor([min(2000, int(0.4 / max((time.perf_counter() - t_w) / 3, 1e-5)))], dtype=torch.int64, device=dev)
@@ -287,15 +304,30 @@ def main():
     clocks.mark()
     eng.prof_reset()
     l0 = eng.launches
-    barrier()
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for e in step_ev:  # torch creates the CUDA event at its first record: do that outside the timed region
+        e.record()
+    # No cyclic-GC pass inside the timed region: with N > 1 a collection on one rank stalls every rank at the
+    # next all-gather.
+    import gc
+    gc.collect()
+    gc.disable()
+    barrier()
     ev0.record()
+    host_t = [time.perf_counter()]
     for i in range(args.steps):
         out = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
         step_ev[i].record()
+        host_t.append(time.perf_counter())
+        if i >= RUN_AHEAD:  # the host stays at most RUN_AHEAD steps ahead of the device (the GPU never runs dry)
+            step_ev[i - RUN_AHEAD].synchronize()
     ev1.record()
     barrier()
+    gc.enable()
     ms_total = ev0.elapsed_time(ev1)
+    if os.environ.get("THR_BENCH_DEBUG"):
+        print(f"[rank {rank}] host ms per step: " + " ".join(f"{(host_t[i + 1] - host_t[i]) * 1e3:.2f}" for i in range(min(args.steps, 8))),
+              file=sys.stderr, flush=True)
     marks = [ev0] + step_ev
     per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     prof = eng.prof_read()

@@ -132,19 +132,24 @@ __device__ uint64_t block_compact_topk_t(uint64_t* keys, int n, int ksel, uint32
 // query order: the sum is part of the definition); after the span's last chunk the accumulator is scanned
 // with 16-byte loads: nonzero slots are zeroed and scores above tau are appended to the candidate list.
 // An append that does not fit leaves its slot in place and raises a flag; the list is then compacted (which raises
-// tau) and the scan repeats, so no threshold warm-up is needed for correctness.  Two CTAs share an SM, so the
-// barrier waits of one overlap with the work of the other.
+// tau) and the scan repeats, so no threshold warm-up is needed for correctness.
+//
+// Shape (measured at 10M docs, batch 256; the THR_SPAN_* macros exist for such sweeps, scripts/build_variant.sh):
+// time is (number of chunk visits) x (consumer warps) x (instructions per visit) at an IPC of ~1.7, so the span is
+// as large as shared memory allows (fewer visits) and the common path of a visit is ~25 instructions; more
+// warps hide more latency even though most of them have no posting in most chunks (a chunk holds a few hundred):
+//   8 warps x 32k docs 3.36 ms | 16 x 32k 2.28 | 24 x 30k 2.18 | 2 CTAs x 8 warps x 16k 2.76 | 3 x 4 x 12k 3.15.
 #ifndef THR_SPAN_DOCS
-#define THR_SPAN_DOCS 32768
+#define THR_SPAN_DOCS 30720
 #endif
 #ifndef THR_SPAN_WARPS
-#define THR_SPAN_WARPS 16
+#define THR_SPAN_WARPS 24
 #endif
 #ifndef THR_SPAN_CHUNK
-#define THR_SPAN_CHUNK 1024
+#define THR_SPAN_CHUNK 1536
 #endif
 #ifndef THR_SPAN_STAGES
-#define THR_SPAN_STAGES 8
+#define THR_SPAN_STAGES 6
 #endif
 #ifndef THR_SPAN_CAP
 #define THR_SPAN_CAP 2048
