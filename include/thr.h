@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 3
+#define THR_ABI_VERSION 4
 
 enum {
   THR_OK = 0,
@@ -221,6 +221,22 @@ int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int
 int thr_merge_topk(thr_handle* h, const double* scores, const int64_t* ids,
                    const int32_t* counts, int G, int B, int k_in, int k_out,
                    double* out_scores, int64_t* out_ids, int32_t* out_count, void* stream);
+
+/* ---- K5 around the product's exchange step (one all-gather per batch) -------------
+ * A rank's message is [scores f64 2*B*k | ids i64 2*B*k | counts i32 2*B] bytes, k = max(k_sem, k_lex):
+ * row block 0 = the rank's semantic lists (thr_dense_topk output), block 1 = its lexical lists
+ * (thr_bm25_topk output), padded with (-inf, -1).  thr_exchange_pack writes it in one launch;
+ * thr_exchange_merge consumes the all-gathered buffer [G][msg bytes] and writes both channels' merged
+ * lists in the formats thr_dense_topk / thr_bm25_topk use, so thr_fuse runs on them unchanged.
+ * New with sharding; same ordering as thr_merge_topk: (score desc, id asc).
+ */
+int64_t thr_exchange_msg_bytes(int B, int k_sem, int k_lex);
+int thr_exchange_pack(thr_handle* h, const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,
+                      const int64_t* l_ids, const float* l_sc, const int32_t* l_cnt, int B, int k_sem,
+                      int k_lex, void* msg, void* stream);
+int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_sem, int k_lex,
+                       int64_t* d_ids, double* d_sc, int32_t* d_cnt, int64_t* l_ids, float* l_sc,
+                       int32_t* l_cnt, void* stream);
 
 #ifdef __cplusplus
 }

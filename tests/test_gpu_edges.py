@@ -96,3 +96,47 @@ def test_merge_with_short_lists(engine):
     m_sc, m_id, m_ct = engine.merge_topk(sc, ids, cnt, 4)
     engine.sync()
     assert m_id[0].tolist() == [10, 3, 7, 11] and m_sc[0].tolist() == [3.0, 2.0, 2.0, 1.0] and int(m_ct[0]) == 4
+
+
+def test_fused_exchange_matches_the_torch_statement(engine):
+    """K5 around the all-gather: thr_exchange_pack / thr_exchange_merge against pipeline.exchange_topk (the
+    same step stated with torch ops, which the gloo test drives) with the oracle merge standing in for K5.
+    G ranks are simulated in one process: every 'rank' packs its own lists, the messages are concatenated."""
+    from oracle import merge as omg
+    dev = engine.device
+    g = torch.Generator().manual_seed(5)
+    G, B, k_sem, k_lex = 3, 7, 10, 6
+    k = max(k_sem, k_lex)
+    ranks = []
+    for r in range(G):
+        d_cnt = torch.randint(0, k_sem + 1, (B,), generator=g, dtype=torch.int32)
+        l_cnt = torch.randint(0, k_lex + 1, (B,), generator=g, dtype=torch.int32)
+        # a small value set makes cross-rank score ties common: order must fall back to the id
+        d_sc = torch.randint(0, 8, (B, k_sem), generator=g).double().sort(dim=1, descending=True).values
+        l_sc = torch.randint(1, 6, (B, k_lex), generator=g).float().sort(dim=1, descending=True).values
+        d_ids = torch.randperm(B * k_sem * G, generator=g)[: B * k_sem].view(B, k_sem) * G + r
+        l_ids = torch.randperm(B * k_lex * G, generator=g)[: B * k_lex].view(B, k_lex) * G + r
+        ranks.append((d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt))
+    nbytes = engine.exchange_msg_bytes(B, k_sem, k_lex)
+    assert nbytes == 2 * (2 * B * k * 8) + 2 * B * 4
+    msgs = []
+    for t in ranks:
+        msg = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        engine.exchange_pack(*[x.to(dev) for x in t], msg)
+        msgs.append(msg)
+    got = engine.exchange_merge(torch.cat(msgs), G, B, k_sem, k_lex)
+    engine.sync()
+    # reference: unpack-free statement of the same merge on the host
+    sc = np.full((G, 2 * B, k), -np.inf)
+    ids = np.full((G, 2 * B, k), -1, dtype=np.int64)
+    cnt = np.zeros((G, 2 * B), dtype=np.int32)
+    for r, (d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt) in enumerate(ranks):
+        sc[r, :B, :k_sem], ids[r, :B, :k_sem], cnt[r, :B] = d_sc.numpy(), d_ids.numpy(), d_cnt.numpy()
+        sc[r, B:, :k_lex], ids[r, B:, :k_lex], cnt[r, B:] = l_sc.double().numpy(), l_ids.numpy(), l_cnt.numpy()
+    w_s, w_i, w_c = omg.merge_topk(sc, ids, cnt, k)
+    d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt = [x.cpu().numpy() for x in got]
+    assert np.array_equal(d_cnt, np.minimum(w_c[:B], k_sem)) and np.array_equal(l_cnt, np.minimum(w_c[B:], k_lex))
+    assert np.array_equal(d_ids, w_i[:B, :k_sem]) and np.array_equal(l_ids, w_i[B:, :k_lex])
+    assert np.array_equal(d_sc, w_s[:B, :k_sem])
+    want_l = np.where(w_i[B:, :k_lex] < 0, 0.0, w_s[B:, :k_lex]).astype(np.float32)
+    assert np.array_equal(l_sc, want_l)

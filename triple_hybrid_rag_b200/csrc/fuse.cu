@@ -461,6 +461,111 @@ __global__ void __launch_bounds__(256) merge_kernel(const double* scores, const 
   }
 }
 
+
+// ---- K5 for the product's exchange step, two launches around the one all-gather -----------------
+// Message of one rank (bytes): [scores f64 2*B*k | ids i64 2*B*k | counts i32 2*B]; row block 0 holds the semantic
+// lists, block 1 the lexical ones, k = max(k_sem, k_lex), lists padded with (-inf, -1).
+__global__ void __launch_bounds__(256) exchange_pack_kernel(const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,
+                                                            const int64_t* l_ids, const float* l_sc, const int32_t* l_cnt,
+                                                            int B, int k_sem, int k_lex, int k, uint8_t* msg) {
+  const size_t n = (size_t)2 * B * k;
+  double* sc = (double*)msg;
+  int64_t* ids = (int64_t*)(msg + n * 8);
+  int32_t* cnt = (int32_t*)(msg + 2 * n * 8);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % k);
+    const int row = (int)(i / k);
+    double s = -INFINITY;
+    int64_t id = -1;
+    if (row < B) {
+      if (j < k_sem) { s = d_sc[(size_t)row * k_sem + j]; id = d_ids[(size_t)row * k_sem + j]; }
+    } else if (j < k_lex) {
+      s = (double)l_sc[(size_t)(row - B) * k_lex + j];
+      id = l_ids[(size_t)(row - B) * k_lex + j];
+    }
+    sc[i] = s;
+    ids[i] = id;
+    if (j == 0) cnt[row] = row < B ? d_cnt[row] : l_cnt[row - B];
+  }
+}
+
+// One CTA per (channel, query): merge the G lists out of the gathered messages, write the channel's final list in
+// the channel's own output format (semantic: f64 scores, -inf padding; lexical: f32 scores, 0 padding as
+// thr_bm25_topk writes them).
+__global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gathered, size_t msg_bytes, int G, int B,
+                                                             int k_sem, int k_lex, int k, int64_t* d_ids, double* d_sc,
+                                                             int32_t* d_cnt, int64_t* l_ids, float* l_sc,
+                                                             int32_t* l_cnt) {
+  __shared__ double s_sc[kMergeMax];
+  __shared__ int64_t s_id[kMergeMax];
+  __shared__ int s_total;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int n = G * k;
+  const size_t nrow = (size_t)2 * B * k;
+  int P = 32;
+  while (P < n) P <<= 1;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < P; i += 256) {
+    double s = -INFINITY;
+    int64_t id = INT64_MAX;
+    if (i < n) {
+      const int g = i / k, j = i % k;
+      const uint8_t* m = gathered + (size_t)g * msg_bytes;
+      const int cnt = ((const int32_t*)(m + 2 * nrow * 8))[row];
+      if (j < cnt) {
+        s = ((const double*)m)[(size_t)row * k + j];
+        id = ((const int64_t*)(m + nrow * 8))[(size_t)row * k + j];
+        ++local;
+      }
+    }
+    s_sc[i] = s;
+    s_id[i] = id;
+  }
+  if (local) atomicAdd(&s_total, local);
+  __syncthreads();
+  auto before = [&](int x, int y) -> bool {
+    int64_t ix = s_id[x], iy = s_id[y];
+    bool vx = ix != INT64_MAX, vy = iy != INT64_MAX;
+    if (vx != vy) return vx;
+    double sx = s_sc[x], sy = s_sc[y];
+    if (sx != sy) return sx > sy;
+    return ix < iy;
+  };
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P >> 1); i += 256) {
+        int lo = ((i / stride) * (stride << 1)) + (i % stride);
+        int hi = lo + stride;
+        bool ascending = ((lo & size) == 0);
+        bool swap = ascending ? before(hi, lo) : before(lo, hi);
+        if (swap) {
+          double ts = s_sc[lo]; s_sc[lo] = s_sc[hi]; s_sc[hi] = ts;
+          int64_t ti = s_id[lo]; s_id[lo] = s_id[hi]; s_id[hi] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (row < B) {
+    const int nout = min(s_total, k_sem);
+    if (tid == 0) d_cnt[row] = nout;
+    for (int i = tid; i < k_sem; i += 256) {
+      d_sc[(size_t)row * k_sem + i] = i < nout ? s_sc[i] : -INFINITY;
+      d_ids[(size_t)row * k_sem + i] = i < nout ? s_id[i] : -1;
+    }
+  } else {
+    const int q = row - B;
+    const int nout = min(s_total, k_lex);
+    if (tid == 0) l_cnt[q] = nout;
+    for (int i = tid; i < k_lex; i += 256) {
+      l_sc[(size_t)q * k_lex + i] = i < nout ? (float)s_sc[i] : 0.f;
+      l_ids[(size_t)q * k_lex + i] = i < nout ? s_id[i] : -1;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -551,5 +656,51 @@ int thr_merge_topk(thr_handle* h, const double* scores, const int64_t* ids, cons
   THR_CHECK_LAUNCH(h, "merge_kernel");
   return THR_OK;
 }
+
+int64_t thr_exchange_msg_bytes(int B, int k_sem, int k_lex) {
+  const int64_t k = k_sem > k_lex ? k_sem : k_lex;
+  return 2 * (2 * (int64_t)B * k * 8) + 2 * (int64_t)B * 4;
+}
+
+int thr_exchange_pack(thr_handle* h, const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,
+                      const int64_t* l_ids, const float* l_sc, const int32_t* l_cnt, int B, int k_sem, int k_lex,
+                      void* msg, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, B >= 0 && k_sem >= 1 && k_lex >= 1, "thr_exchange_pack: bad sizes");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, d_ids && d_sc && d_cnt && l_ids && l_sc && l_cnt && msg, "thr_exchange_pack: NULL argument");
+  THR_REQUIRE(h, ((uintptr_t)msg & 7u) == 0, "thr_exchange_pack: msg must be 8-byte aligned");
+  const int k = k_sem > k_lex ? k_sem : k_lex;
+  const size_t n = (size_t)2 * B * k;
+  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  const int tok = thr_prof_begin(h, THR_PROF_MERGE, (cudaStream_t)stream);
+  exchange_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, B, k_sem, k_lex,
+                                                                 k, (uint8_t*)msg);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
+  THR_CHECK_LAUNCH(h, "exchange_pack_kernel");
+  return THR_OK;
+}
+
+int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_sem, int k_lex, int64_t* d_ids,
+                       double* d_sc, int32_t* d_cnt, int64_t* l_ids, float* l_sc, int32_t* l_cnt, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, G >= 1 && B >= 0 && k_sem >= 1 && k_lex >= 1, "thr_exchange_merge: bad sizes");
+  if (B == 0) return THR_OK;
+  const int k = k_sem > k_lex ? k_sem : k_lex;
+  THR_REQUIRE(h, (int64_t)G * k <= kMergeMax, "thr_exchange_merge: G*k = %lld exceeds %d", (long long)G * k, kMergeMax);
+  THR_REQUIRE(h, k_sem <= 256 && k_lex <= 256, "thr_exchange_merge: k > 256");
+  THR_REQUIRE(h, gathered && d_ids && d_sc && d_cnt && l_ids && l_sc && l_cnt, "thr_exchange_merge: NULL argument");
+  THR_REQUIRE(h, ((uintptr_t)gathered & 7u) == 0, "thr_exchange_merge: buffer must be 8-byte aligned");
+  const int tok = thr_prof_begin(h, THR_PROF_MERGE, (cudaStream_t)stream);
+  exchange_merge_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)gathered,
+                                                                 (size_t)thr_exchange_msg_bytes(B, k_sem, k_lex), G, B, k_sem,
+                                                                 k_lex, k, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
+  THR_CHECK_LAUNCH(h, "exchange_merge_kernel");
+  return THR_OK;
+}
+
 
 }  // extern "C"

@@ -242,3 +242,38 @@ class Engine:
         self._check(self._lib.thr_merge_topk(self._h, _ptr(scores), _ptr(ids), _ptr(counts), G, B, k_in, k_out,
                                              _ptr(o_sc), _ptr(o_ids), _ptr(o_cnt), self._stream()))
         return o_sc, o_ids, o_cnt
+
+    # ---- K5 around the sharded exchange ----
+    def exchange_msg_bytes(self, B: int, k_sem: int, k_lex: int) -> int:
+        return int(self._lib.thr_exchange_msg_bytes(B, k_sem, k_lex))
+
+    def exchange_pack(self, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, msg: torch.Tensor) -> torch.Tensor:
+        """This rank's lists of both channels -> one byte message (layout in include/thr.h), one launch."""
+        B, k_sem = d_ids.shape
+        k_lex = l_ids.shape[1]
+        d_ids = self._dev(d_ids, torch.int64, "d_ids"); d_sc = self._dev(d_sc, torch.float64, "d_sc")
+        d_cnt = self._dev(d_cnt, torch.int32, "d_cnt"); l_ids = self._dev(l_ids, torch.int64, "l_ids")
+        l_sc = self._dev(l_sc, torch.float32, "l_sc"); l_cnt = self._dev(l_cnt, torch.int32, "l_cnt")
+        msg = self._dev(msg, torch.uint8, "msg")
+        if msg.numel() != self.exchange_msg_bytes(B, k_sem, k_lex):
+            raise ValueError("exchange_pack: msg has the wrong size")
+        self._check(self._lib.thr_exchange_pack(self._h, _ptr(d_ids), _ptr(d_sc), _ptr(d_cnt), _ptr(l_ids), _ptr(l_sc),
+                                                _ptr(l_cnt), B, k_sem, k_lex, _ptr(msg), self._stream()))
+        return msg
+
+    def exchange_merge(self, gathered: torch.Tensor, G: int, B: int, k_sem: int, k_lex: int):
+        """All-gathered messages [G, msg bytes] -> (d_ids, d_sc f64, d_cnt, l_ids, l_sc f32, l_cnt), one launch."""
+        gathered = self._dev(gathered, torch.uint8, "gathered")
+        if gathered.numel() != G * self.exchange_msg_bytes(B, k_sem, k_lex):
+            raise ValueError("exchange_merge: gathered has the wrong size")
+        dev = self.device
+        d_ids = torch.empty((B, k_sem), dtype=torch.int64, device=dev)
+        d_sc = torch.empty((B, k_sem), dtype=torch.float64, device=dev)
+        d_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        l_ids = torch.empty((B, k_lex), dtype=torch.int64, device=dev)
+        l_sc = torch.empty((B, k_lex), dtype=torch.float32, device=dev)
+        l_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        self._check(self._lib.thr_exchange_merge(self._h, _ptr(gathered), G, B, k_sem, k_lex, _ptr(d_ids), _ptr(d_sc),
+                                                 _ptr(d_cnt), _ptr(l_ids), _ptr(l_sc), _ptr(l_cnt), self._stream()))
+        return d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt
+

@@ -152,8 +152,17 @@ class TripleHybridSearcher:
         return (ids.reshape(-1), off, None)
 
     def _exchange(self, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt):
-        return exchange_topk(self.group, self.world, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt,
-                             self.engine.merge_topk)
+        """The exchange step on the GPU: pack (one launch) -> ONE NCCL all-gather -> merge of both channels (one
+        launch).  Same message layout and ordering as exchange_topk above, which states it with torch ops and is
+        what the gloo test drives; tests/test_gpu_edges.py checks the two against each other."""
+        import torch.distributed as dist
+        eng = self.engine
+        nbytes = eng.exchange_msg_bytes(B, k_sem, k_lex)
+        msg = torch.empty((nbytes,), dtype=torch.uint8, device=eng.device)
+        eng.exchange_pack(d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, msg)
+        gathered = torch.empty((self.world * nbytes,), dtype=torch.uint8, device=eng.device)
+        dist.all_gather_into_tensor(gathered, msg, group=self.group)
+        return eng.exchange_merge(gathered, self.world, B, k_sem, k_lex)
 
     # ---- one batch, HOST tensors in / out (the end-to-end path) ----------------------------
     def _pin(self, name: str, like: torch.Tensor) -> torch.Tensor:
