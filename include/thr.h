@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 4
+#define THR_ABI_VERSION 5
 
 enum {
   THR_OK = 0,
@@ -109,6 +109,18 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin,
                    int64_t* out_ids, double* out_scores, int32_t* out_count, float* out_gap,
                    void* stream);
 
+/* Tag filter of the semantic channel — the `collection` predicate of rag2_semantic_search
+ * (database/migrations/20260114_rag2_schema.sql:404-406) evaluated inside the scan instead of by
+ * over-fetching.  tags [N] uint16 on the device (8-byte aligned, stays resident; NULL clears): one tag per
+ * chunk, e.g. the collection id.  thr_dense_topk_tagged is thr_dense_topk restricted, per query, to the
+ * chunks whose tag equals want[q] (want [B] int32 on the device; < 0 = no restriction; NULL = plain
+ * thr_dense_topk): the exact top-k of the filtered corpus, out_count = min(k, eligible chunks).
+ */
+int thr_dense_tags_set(thr_handle* h, const uint16_t* tags);
+int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin, const int32_t* want,
+                          int64_t* out_ids, double* out_scores, int32_t* out_count, float* out_gap,
+                          void* stream);
+
 /* ---- K2: lexical channel — BM25 top-k over a blocked CSR inverted index ----------
  * Replaces RAG2Retriever._lexical_search -> RPC rag2_lexical_search
  *   src/voice_agent/rag2/retrieval.py:273-292
@@ -142,6 +154,13 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
  */
 int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
                   int64_t* out_ids, float* out_scores, int32_t* out_count, void* stream);
+
+/* Tag filter of the lexical channel (the `collection` predicate of rag2_lexical_search, :368-370): same
+ * contract as thr_dense_tags_set / thr_dense_topk_tagged; tags [n_docs] uint16 on the device. */
+int thr_bm25_tags_set(thr_handle* h, const uint16_t* tags);
+int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                         const int32_t* want, int64_t* out_ids, float* out_scores, int32_t* out_count,
+                         void* stream);
 
 /* ---- K3: weighted RRF fusion + safety threshold + conformal denoise ---------------
  * Replaces, bit-exactly in fp64:

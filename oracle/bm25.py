@@ -54,9 +54,11 @@ class CsrIndex:
         return CsrIndex(indptr, doc.astype(np.int64), imp, idf.astype(np.float32), n_docs)
 
 
-def bm25_topk(index: CsrIndex, queries: Sequence[Sequence[int]], k: int, id_base: int = 0
+def bm25_topk(index: CsrIndex, queries: Sequence[Sequence[int]], k: int, id_base: int = 0, tags=None, want=None
               ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Returns ids [B,k] int64 (-1 padded), scores [B,k] float32, count [B] int32."""
+    """Returns ids [B,k] int64 (-1 padded), scores [B,k] float32, count [B] int32.
+    tags [n_docs] / want [B]: the collection predicate of rag2_lexical_search (20260114_rag2_schema.sql:368-370) —
+    query q only sees docs with tags == want[q] (want < 0: all)."""
     B = len(queries)
     out_i = np.full((B, k), -1, dtype=np.int64)
     out_s = np.zeros((B, k), dtype=np.float32)
@@ -72,7 +74,10 @@ def bm25_topk(index: CsrIndex, queries: Sequence[Sequence[int]], k: int, id_base
             d = index.doc[lo:hi]
             contrib = (index.idf[t] * index.imp[lo:hi]).astype(np.float32)  # fp32 multiply
             acc[d] = acc[d] + contrib                                        # fp32 add; docs unique per list
-        hit = np.nonzero(acc > 0)[0]
+        ok = acc > 0
+        if want is not None and int(want[qi]) >= 0:
+            ok &= np.asarray(tags) == int(want[qi])
+        hit = np.nonzero(ok)[0]
         if hit.size == 0:
             continue
         order = np.lexsort((hit, -acc[hit].astype(np.float64)))[:k]

@@ -18,9 +18,11 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return r.astype(np.uint32).view(np.float32)
 
 
-def dense_topk(Q: np.ndarray, X: np.ndarray, k: int, id_base: int = 0, block: int = 65536):
+def dense_topk(Q: np.ndarray, X: np.ndarray, k: int, id_base: int = 0, block: int = 65536, tags=None, want=None):
     """Q [B,D], X [N,D] already bf16-representable (fp32 or fp64 storage).
-    Returns ids [B,k] int64 (-1 padded), scores [B,k] float64."""
+    Returns ids [B,k] int64 (-1 padded), scores [B,k] float64.
+    tags [N] / want [B]: the collection predicate of rag2_semantic_search (20260114_rag2_schema.sql:404-406) —
+    query q only sees chunks with tags == want[q] (want < 0: all); slots past the eligible count are (-1, -inf)."""
     Q64 = np.asarray(Q, dtype=np.float64)
     B, N = Q64.shape[0], X.shape[0]
     kk = min(k, N)
@@ -29,6 +31,9 @@ def dense_topk(Q: np.ndarray, X: np.ndarray, k: int, id_base: int = 0, block: in
     for s in range(0, N, block):
         Xb = np.asarray(X[s:s + block], dtype=np.float64)
         S = Q64 @ Xb.T
+        if want is not None:
+            w = np.asarray(want)[:, None]
+            S = np.where((w < 0) | (np.asarray(tags[s:s + block])[None, :] == w), S, -np.inf)
         ids = np.broadcast_to(np.arange(s, s + Xb.shape[0], dtype=np.int64), S.shape)
         best_s = np.concatenate([best_s, S], axis=1)
         best_i = np.concatenate([best_i, ids], axis=1)
@@ -41,6 +46,6 @@ def dense_topk(Q: np.ndarray, X: np.ndarray, k: int, id_base: int = 0, block: in
     best_i = np.take_along_axis(best_i, order, 1)
     out_i = np.full((B, k), -1, dtype=np.int64)
     out_s = np.full((B, k), -np.inf)
-    out_i[:, :kk] = best_i + id_base
+    out_i[:, :kk] = np.where(np.isneginf(best_s), -1, best_i + id_base)
     out_s[:, :kk] = best_s
     return out_i, out_s

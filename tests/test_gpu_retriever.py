@@ -198,9 +198,18 @@ def test_resident_index_end_to_end_vs_oracle(engine, settings):
     assert [x["child_id"] for x in rows] == [f"c{i}" for i in bi[0, :bc[0]]]
     assert np.array_equal(np.array([x["rank"] for x in rows], dtype=np.float32), bs[0, :bc[0]])
     assert asyncio.run(r._lexical_search(["nosuchword"], None, 50)) == []
-    # collection predicate (post-filter)
+    # collection predicate, evaluated inside K2 / K1: the exact top-10 of collection "b"
     rows_b = asyncio.run(r._lexical_search(kw, "b", 10))
     assert rows_b and all(chunks[ix.id_of[x["child_id"]]]["collection"] == "b" for x in rows_b)
+    tags = np.array([0 if c["collection"] == "a" else 1 for c in chunks])
+    fi, fs, fc = ob.bm25_topk(orc, [[ix.vocab["w3"], ix.vocab["w17"], ix.vocab["w150"]]], 10, tags=tags, want=[1])
+    assert [x["child_id"] for x in rows_b] == [f"c{i}" for i in fi[0, :fc[0]]]
+    assert asyncio.run(r._lexical_search(kw, "no-such-collection", 10)) == []
+    sem_b = asyncio.run(r._semantic_search("find me", "b", 10))
+    assert len(sem_b) == 10 and all(chunks[ix.id_of[x["child_id"]]]["collection"] == "b" for x in sem_b)
+    sem_all = asyncio.run(r._semantic_search("find me", None, 300))
+    assert [x["child_id"] for x in sem_b] == [x["child_id"] for x in sem_all
+                                              if chunks[ix.id_of[x["child_id"]]]["collection"] == "b"][:10]
 
     # whole pipeline, MaxSim rerank included, against the oracle
     settings.rag2_rerank_top_k, settings.rag2_safety_threshold, settings.rag2_denoise_alpha = 20, 0.0, 0.0

@@ -47,6 +47,8 @@ struct Bm25Args {
   int B, k;
   uint64_t* part_keys;    // [max_units][k] sorted descending
   int32_t* part_cnt;      // [max_units]
+  const uint16_t* tags;   // [n_docs] nullable: per-doc tag (collection id) for filtered queries
+  const int32_t* want;    // [B] nullable: tag a query's docs must carry, < 0 = any
   thr_dev_status* status;
 };
 
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
   volatile int* v_ovf = &s_int[3];
   float tau = 0.f;
   int unit = -1;
+  int want = -1;      // tag filter of the current unit's query (< 0: none)
   uint32_t s = 0, ph = 0;
   auto compact = [&](int n) {
     const uint64_t T = block_compact_topk_t<kSpanThreads, kSpanCap, kSpanBar>(cand, n, a.k, hist, s_prefix, &s_int[0],
@@ -385,7 +388,11 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
     if (lane == 0) mbar_arrive(empty_u + s * 8u);
     if (++s == kStages) { s = 0; ph ^= 1u; }
     if (!(fl & (kFNewUnit | kFEndSpan | kFEndUnit | kFExit))) continue;
-    if (fl & kFNewUnit) { unit = (int)dw; tau = 0.f; }
+    if (fl & kFNewUnit) {
+      unit = (int)dw;
+      tau = 0.f;
+      want = (a.tags && a.want) ? a.want[a.units[unit].q] : -1;
+    }
 
     if (fl & kFEndSpan) {
       bar_group<kSpanThreads, kSpanBar>();                    // every add of the span has landed
@@ -418,7 +425,9 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float x = __uint_as_float(v[c]);
-              if (x > tau) {
+              // a doc outside the query's tag is dropped here: it never enters the list, so tau is learnt from
+              // eligible docs only and the result is the exact top-k of the filtered corpus
+              if (x > tau && (want < 0 || (int)a.tags[doc + c] == want)) {
                 const int pos = atomicAdd(&s_int[2], 1);
                 if (pos < kSpanCap) cand[pos] = pack_key(x, doc + c);
                 else { *v_ovf = 1; z[c] = v[c]; }              // stays in the accumulator for the next scan
@@ -482,9 +491,11 @@ __global__ void bm25_df_kernel(const int64_t* skip, int n_blk, int V, int64_t* d
   df[t] = skip[(size_t)(t + 1) * n_blk] - skip[(size_t)t * n_blk];
 }
 
-// cost[q] = total postings of the query's terms.
+// cost[q] = total postings of the query's terms + term_cost per (term with postings, range): the kernel's time
+// follows the number of (term, span) visits at least as much as the number of postings.
 __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, const int64_t* df, int V,
-                                 int B, unsigned long long* keys, thr_dev_status* status) {
+                                 int B, int n_blk, long long term_cost, unsigned long long* keys,
+                                 thr_dev_status* status) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
   // more terms than the kernel has lanes for: reported by thr_sync, never silently truncated
@@ -492,7 +503,7 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
   long long c = 0;
   for (int i = q_off[q]; i < q_off[q + 1]; ++i) {
     int t = q_terms[i];
-    if (t >= 0 && t < V) c += df[t];
+    if (t >= 0 && t < V && df[t] > 0) c += df[t] + term_cost * n_blk;
   }
   if (c > 0xffffffffll) c = 0xffffffffll;
   keys[q] = ((unsigned long long)c << 32) | (unsigned)(0xffffffffu - (unsigned)q);
@@ -500,7 +511,8 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
 // per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
-constexpr unsigned long long kSpanRangeCost = 200;   // the scan of a range is worth about this many postings
+constexpr unsigned long long kSpanRangeCost = 400;   // the scan of a range is worth about this many postings
+constexpr long long kSpanTermCost = 75;         // per (term, range) on top of the term's postings
 constexpr int kSpanUnitsPerCta = 2;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_slots, unsigned long long kRangeCost,
@@ -628,6 +640,7 @@ struct thr_bm25_state {
   int n_blk, blk_docs, blk_shift, V;
   int64_t id_base;
   int64_t* df;  // [V] device
+  const uint16_t* tags;  // [n_docs] device, nullable
 };
 
 void thr_bm25_state_free(thr_handle* h) {
@@ -675,12 +688,26 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
   return THR_OK;
 }
 
+int thr_bm25_tags_set(thr_handle* h, const uint16_t* tags) {
+  if (!h) return THR_EINVAL;
+  if (!h->bm25) return thr_fail(h, THR_ENOINDEX, "thr_bm25_tags_set: call thr_bm25_index_set first");
+  h->bm25->tags = tags;
+  return THR_OK;
+}
+
 int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
                   int64_t* out_ids, float* out_scores, int32_t* out_count, void* stream) {
+  return thr_bm25_topk_tagged(h, q_terms, q_off, B, k, nullptr, out_ids, out_scores, out_count, stream);
+}
+
+int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                         const int32_t* want, int64_t* out_ids, float* out_scores, int32_t* out_count,
+                         void* stream) {
   if (!h) return THR_EINVAL;
   cudaSetDevice(h->device);
   thr_bm25_state* st = h->bm25;
   if (!st) return thr_fail(h, THR_ENOINDEX, "thr_bm25_topk: call thr_bm25_index_set first");
+  THR_REQUIRE(h, want == nullptr || st->tags != nullptr, "thr_bm25_topk_tagged: call thr_bm25_tags_set first");
   THR_REQUIRE(h, B >= 0 && k >= 1 && k <= kMaxSelB, "thr_bm25_topk: need 1 <= k <= %d", kMaxSelB);
   if (B == 0) return THR_OK;
   THR_REQUIRE(h, q_terms && q_off && out_ids && out_scores && out_count, "thr_bm25_topk: NULL argument");
@@ -708,12 +735,13 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   uint64_t* part_keys = (uint64_t*)(ws + o_pkeys);
 
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
-  bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, keys, h->d_status);
-  THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
+
   // Work is cut into about `grid * units_per_cta` units of equal cost (heaviest first, fetched dynamically).
   static int units_per_cta = 0;
-  static long long range_cost = -1;
+  static long long range_cost = -1, term_cost = 0;
   if (!units_per_cta) {
+    const char* t = getenv("THR_BM25_TERM_COST");
+    term_cost = t ? atoll(t) : (long long)kSpanTermCost;
     const char* e = getenv("THR_BM25_UNITS_PER_SM");   // measured flat between 1 and 4 at 10M docs
     units_per_cta = e ? atoi(e) : kSpanUnitsPerCta;
     if (units_per_cta < 1) units_per_cta = 1;
@@ -721,6 +749,9 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
     range_cost = e ? atoll(e) : (long long)kSpanRangeCost;
   }
   const int grid = kSpanCtas * h->num_sms;
+  bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, st->n_blk, term_cost, keys,
+                                                   h->d_status);
+  THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
   bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, grid * units_per_cta, (unsigned long long)range_cost, units,
                                       unit_base, total_units, counter);
   THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
@@ -733,6 +764,7 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
   a.n_blk = st->n_blk; a.blk_docs = st->blk_docs; a.blk_shift = st->blk_shift; a.V = st->V;
   a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.units = units; a.total_units = total_units;
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
+  a.tags = want ? st->tags : nullptr; a.want = want;
   a.status = h->d_status;
   THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmem));
   THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

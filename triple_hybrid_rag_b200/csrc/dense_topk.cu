@@ -58,6 +58,8 @@ struct ScoreArgs {
   int32_t* cnt;     // [n_clusters][Bpad]
   const float* tau_init;  // [Bpad] nullable: per-query lower bound of the K'-th best score (seed pass)
   int seed_mode;          // seed pass: leave the lists uncompacted (<= kSeedTiles * kTileN entries each)
+  const uint16_t* tags;   // [N] nullable: per-chunk tag (collection id) for filtered queries
+  const int32_t* want;    // [B] nullable: tag a query's chunks must carry, < 0 = any
   thr_dev_status* status;
 };
 
@@ -265,6 +267,9 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       // padding rows of the query block never pass; a seeded threshold is a valid lower bound of the
       // global K'-th best score, so nothing that could reach the final top-k is filtered
       float tau = row_valid ? (a.tau_init ? a.tau_init[row] : -CUDART_INF_F) : CUDART_INF_F;
+      // tag filter: a chunk outside the query's tag is never appended, so every threshold (seed pass included) is
+      // learnt from eligible chunks only and the result is the exact top-k of the filtered corpus
+      const int want = (row_valid && a.tags && a.want) ? a.want[row] : -1;
       int cnt = 0;
       for (int64_t t = tile_lo; t < tile_hi && ok; ++t, ++tcount) {
         const int acc = tcount & 1;
@@ -297,14 +302,18 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               const uint32_t inv0 = ~(uint32_t)(col0 + c * 32);  // ~(col0 + c*32 + j) == inv0 - j
 // Four columns at a time: max + one compare + one warp vote; the (predicated) appends run only when
 // some lane of the warp passes — after warm-up that is ~ 128*K'/seen of the groups.
-#define P1(j) if (__uint_as_float(r[j]) > tau) *wptr++ = ((uint64_t)r[j] << 32) | (uint64_t)(inv0 - (uint32_t)(j));
+#define P1(j, tg)                                                                                  \
+  if (__uint_as_float(r[j]) > tau && (want < 0 || (int)(tg) == want))                              \
+    *wptr++ = ((uint64_t)r[j] << 32) | (uint64_t)(inv0 - (uint32_t)(j));
 #define P(j)                                                                                       \
   {                                                                                                \
     const float m4 = fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),                \
                            fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));           \
     if (__any_sync(0xffffffffu, m4 > tau)) {                                                       \
       asm volatile("" ::: "memory"); /* keep this a real (warp-uniform) branch */                  \
-      P1(j) P1(j + 1) P1(j + 2) P1(j + 3)                                                          \
+      ushort4 tg = make_ushort4(0, 0, 0, 0);                                                       \
+      if (a.tags) tg = __ldg((const ushort4*)(a.tags + col0 + c * 32 + (j))); /* 8-byte aligned */ \
+      P1(j, tg.x) P1(j + 1, tg.y) P1(j + 2, tg.z) P1(j + 3, tg.w)                                  \
     }                                                                                              \
   }
               P(0); P(4); P(8); P(12); P(16); P(20); P(24); P(28);
@@ -323,7 +332,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int col = c * 32 + j;
-                if (__uint_as_float(r[j]) > tau && col < ncols)
+                if (__uint_as_float(r[j]) > tau && col < ncols && (want < 0 || (int)a.tags[col0 + col] == want))
                   *wptr++ = ((uint64_t)r[j] << 32) | (uint64_t)(~(uint32_t)(col0 + col));
               }
             }
@@ -604,6 +613,7 @@ struct thr_dense_state {
   int64_t id_base;
   CUtensorMap map_x;
   int cta_group;  // 2 (pair) or 1; THR_DENSE_CTA_GROUP overrides for bring-up
+  const uint16_t* tags;  // [N] device, nullable
 };
 
 void thr_dense_state_free(thr_handle* h) {
@@ -657,12 +667,27 @@ int thr_dense_index_set(thr_handle* h, const void* X, int64_t N, int D, int64_t 
   return THR_OK;
 }
 
+int thr_dense_tags_set(thr_handle* h, const uint16_t* tags) {
+  if (!h) return THR_EINVAL;
+  if (!h->dense) return thr_fail(h, THR_ENOINDEX, "thr_dense_tags_set: call thr_dense_index_set first");
+  THR_REQUIRE(h, ((uintptr_t)tags & 7u) == 0, "thr_dense_tags_set: tags must be 8-byte aligned");
+  h->dense->tags = tags;
+  return THR_OK;
+}
+
 int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64_t* out_ids,
                    double* out_scores, int32_t* out_count, float* out_gap, void* stream) {
+  return thr_dense_topk_tagged(h, Q, B, k, margin, nullptr, out_ids, out_scores, out_count, out_gap, stream);
+}
+
+int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin, const int32_t* want,
+                          int64_t* out_ids, double* out_scores, int32_t* out_count, float* out_gap,
+                          void* stream) {
   if (!h) return THR_EINVAL;
   cudaSetDevice(h->device);
   thr_dense_state* st = h->dense;
   if (!st) return thr_fail(h, THR_ENOINDEX, "thr_dense_topk: call thr_dense_index_set first");
+  THR_REQUIRE(h, want == nullptr || st->tags != nullptr, "thr_dense_topk_tagged: call thr_dense_tags_set first");
   THR_REQUIRE(h, B >= 0 && k >= 1 && margin >= 0, "thr_dense_topk: bad B/k/margin");
   if (B == 0) return THR_OK;
   THR_REQUIRE(h, k + margin <= kMaxSel, "thr_dense_topk: k + margin = %d exceeds %d", k + margin, kMaxSel);
@@ -691,6 +716,8 @@ int thr_dense_topk(thr_handle* h, const void* Q, int B, int k, int margin, int64
   a.cand = (uint64_t*)ws; a.cnt = (int32_t*)(ws + cand_bytes); a.status = h->d_status;
   a.tau_init = nullptr;
   a.seed_mode = 0;
+  a.tags = want ? st->tags : nullptr;
+  a.want = want;
   float* tau_seed = (float*)(ws + cand_bytes + cnt_bytes);
 
   FinalArgs f;

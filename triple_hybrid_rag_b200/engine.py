@@ -96,17 +96,31 @@ class Engine:
         self._keep["X"] = X
         self._check(self._lib.thr_dense_index_set(self._h, _ptr(X), X.shape[0], X.shape[1], id_base))
 
-    def dense_topk(self, Q: torch.Tensor, k: int, margin: int = 28
+    def dense_tags_set(self, tags: Optional[torch.Tensor]):
+        """Per-chunk tags (uint16 collection ids, [N] on the device) for dense_topk(want=...); None clears."""
+        if tags is not None:
+            tags = self._dev(tags, torch.uint16, "tags")
+            if tags.numel() != self._keep["X"].shape[0]:
+                raise ValueError("tags must have one entry per chunk")
+        self._keep["dense_tags"] = tags
+        self._check(self._lib.thr_dense_tags_set(self._h, _ptr(tags)))
+
+    def dense_topk(self, Q: torch.Tensor, k: int, margin: int = 28, want: Optional[torch.Tensor] = None
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> ids [B,k] int64, scores [B,k] float64, count [B] int32, gap [B] float32."""
+        """-> ids [B,k] int64, scores [B,k] float64, count [B] int32, gap [B] float32.
+        want: int32 [B] on the device — restrict query q to chunks tagged want[q] (< 0: no restriction)."""
         Q = self._dev(Q, torch.bfloat16, "Q")
         B = Q.shape[0]
+        if want is not None:
+            want = self._dev(want, torch.int32, "want")
+            if want.numel() != B:
+                raise ValueError("want must have one entry per query")
         ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((B, k), dtype=torch.float64, device=self.device)
         cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
         gap = torch.empty((B,), dtype=torch.float32, device=self.device)
-        self._check(self._lib.thr_dense_topk(self._h, _ptr(Q), B, k, margin, _ptr(ids), _ptr(sc), _ptr(cnt),
-                                             _ptr(gap), self._stream()))
+        self._check(self._lib.thr_dense_topk_tagged(self._h, _ptr(Q), B, k, margin, _ptr(want), _ptr(ids), _ptr(sc),
+                                                    _ptr(cnt), _ptr(gap), self._stream()))
         return ids, sc, cnt, gap
 
     # -- K2 BM25 ----------------------------------------------------------------------------
@@ -122,17 +136,28 @@ class Engine:
         self._check(self._lib.thr_bm25_index_set(self._h, _ptr(skip), _ptr(postings), _ptr(idf), n_docs, n_blk,
                                                  blk_docs, V, id_base))
 
-    def bm25_topk(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int
+    def bm25_tags_set(self, tags: Optional[torch.Tensor]):
+        """Per-doc tags (uint16, [n_docs] on the device) for bm25_topk(want=...); None clears."""
+        if tags is not None:
+            tags = self._dev(tags, torch.uint16, "tags")
+        self._keep["bm25_tags"] = tags
+        self._check(self._lib.thr_bm25_tags_set(self._h, _ptr(tags)))
+
+    def bm25_topk(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int, want: Optional[torch.Tensor] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> ids [B,k] int64, scores [B,k] float32, count [B] int32."""
+        """-> ids [B,k] int64, scores [B,k] float32, count [B] int32.  want: as in dense_topk."""
         q_terms = self._dev(q_terms, torch.int32, "q_terms")
         q_off = self._dev(q_off, torch.int32, "q_off")
         B = q_off.numel() - 1
+        if want is not None:
+            want = self._dev(want, torch.int32, "want")
+            if want.numel() != B:
+                raise ValueError("want must have one entry per query")
         ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((B, k), dtype=torch.float32, device=self.device)
         cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
-        self._check(self._lib.thr_bm25_topk(self._h, _ptr(q_terms), _ptr(q_off), B, k, _ptr(ids), _ptr(sc),
-                                            _ptr(cnt), self._stream()))
+        self._check(self._lib.thr_bm25_topk_tagged(self._h, _ptr(q_terms), _ptr(q_off), B, k, _ptr(want), _ptr(ids),
+                                                   _ptr(sc), _ptr(cnt), self._stream()))
         return ids, sc, cnt
 
     # -- K3 fusion --------------------------------------------------------------------------

@@ -108,6 +108,12 @@ class TripleHybridSearcher:
         self.engine.dense_index_set(X_local, id_base=id_base)
         self.has_dense = True
 
+    def set_tags(self, tags_local: Optional[torch.Tensor]):
+        """Per-chunk tags of this shard (uint16, e.g. collection ids) for search(want=...): the reference's
+        `collection` predicate (20260114_rag2_schema.sql:368-370, :404-406) evaluated inside K1 and K2."""
+        self.engine.dense_tags_set(tags_local)
+        self.engine.bm25_tags_set(tags_local)
+
     def set_bm25(self, index: BM25Index, id_base: int = 0):
         d = index.to(self.engine.device)
         self.bm25 = d
@@ -118,11 +124,13 @@ class TripleHybridSearcher:
     def search(self, Q: torch.Tensor, q_terms: torch.Tensor, q_off: torch.Tensor,
                graph_ids: Optional[torch.Tensor], weights: Optional[torch.Tensor] = None,
                k_sem: int = 100, k_lex: int = 100, top_k: int = 100, margin: int = 28,
-               tie_mode: int = _lib.TIE_CHUNK_ID, rrf_k: int = 60) -> SearchOutput:
+               tie_mode: int = _lib.TIE_CHUNK_ID, rrf_k: int = 60, want: Optional[torch.Tensor] = None) -> SearchOutput:
+        """want: int32 [B] on the device — per query, the tag its semantic and lexical hits must carry (< 0: any);
+        needs set_tags.  The graph list is an input and is taken as given."""
         eng, dev = self.engine, self.engine.device
         B = Q.shape[0]
-        d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin)
-        l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex)
+        d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin, want=want)
+        l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex, want=want)
         if self.world > 1:
             d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt = self._exchange(B, k_sem, k_lex, d_ids, d_sc, d_cnt,
                                                                     l_ids, l_sc, l_cnt)

@@ -147,6 +147,26 @@ class ResidentIndex:
         # late-interaction token store (optional)
         self.token_store = None if token_store is None else token_store.to(torch.bfloat16).to(dev).contiguous()
         self.token_lens = None if token_lens is None else token_lens.to(torch.int32).to(dev).contiguous()
+        self._set_tags()
+
+    def _set_tags(self) -> None:
+        """Collection names -> uint16 tags resident next to the indexes: the reference's `collection` predicate
+        (20260114_rag2_schema.sql:368-370, :404-406) is evaluated inside K1 / K2 (thr_*_topk_tagged)."""
+        names = sorted({c for c in self.collections if c is not None})
+        if len(names) >= 0xffff:
+            raise ValueError("at most 65534 collections per resident index")
+        self.tag_of = {c: i for i, c in enumerate(names)}
+        tags = torch.tensor([self.tag_of.get(c, 0xffff) for c in self.collections], dtype=torch.int32)
+        self.tags = tags.to(torch.uint16).to(self.engine.device).contiguous()
+        self.engine.dense_tags_set(self.tags)
+        self.engine.bm25_tags_set(self.tags)
+
+    def want(self, collection: Optional[str]) -> Optional[torch.Tensor]:
+        """The per-query filter argument of the tagged kernels for one query (None: no filter).  A collection no
+        chunk carries maps to a tag no chunk carries, i.e. to an empty result, like the SQL predicate."""
+        if collection is None:
+            return None
+        return torch.tensor([self.tag_of.get(collection, 0xfffe)], dtype=torch.int32, device=self.engine.device)
 
     # ---- persistence (SURVEY.md 8f row 1): start a retriever without re-reading / re-embedding the corpus ----
     def save(self, path) -> None:
@@ -180,6 +200,7 @@ class ResidentIndex:
                               self.bm25.V)
         self.token_store = None if d["token_store"] is None else d["token_store"].to(dev).contiguous()
         self.token_lens = None if d["token_lens"] is None else d["token_lens"].to(dev).contiguous()
+        self._set_tags()
         return self
 
     def row_dict(self, i: int, **extra) -> Dict[str, Any]:
@@ -280,15 +301,6 @@ class GpuRAG2Retriever:
         return list(merged.values())
 
     # ---- channels ---------------------------------------------------------------------------------
-    def _filter_collection(self, ids: Sequence[int], collection: Optional[str], limit: int) -> List[int]:
-        if collection is None:
-            return list(ids)[:limit]
-        return [i for i in ids if self.index.collections[i] == collection][:limit]
-
-    def _fetch(self, limit: int, collection: Optional[str]) -> int:
-        # collection predicates are applied after the kernel: over-fetch, then filter
-        return limit if collection is None else min(228, max(limit * 4, limit))
-
     async def _lexical_search(self, keywords: List[str], collection: Optional[str], limit: int) -> List[Dict[str, Any]]:
         """Reference: retrieval.py:273-292 (query = the keywords joined by spaces, top-`limit` rows, best first).
         Rows carry `rank` = the BM25 score, as the RPC returns its ts_rank_cd."""
@@ -297,25 +309,21 @@ class GpuRAG2Retriever:
         if not terms:
             return []
         qt, qo = pack_queries([terms], eng.device)
-        ids, sc, cnt = eng.bm25_topk(qt, qo, min(self._fetch(limit, collection), 256))
+        ids, sc, cnt = eng.bm25_topk(qt, qo, min(limit, 256), want=ix.want(collection))   # predicate inside K2
         eng.sync()
         n = int(cnt[0])
-        ids, sc = ids[0, :n].tolist(), sc[0, :n].tolist()
-        score_of = dict(zip(ids, sc))
-        return [ix.row_dict(i, rank=score_of[i]) for i in self._filter_collection(ids, collection, limit)]
+        return [ix.row_dict(i, rank=r) for i, r in zip(ids[0, :n].tolist(), sc[0, :n].tolist())]
 
     async def _semantic_search(self, query_text: str, collection: Optional[str], limit: int) -> List[Dict[str, Any]]:
         """Reference: retrieval.py:294-314 (embed the query, top-`limit` by cosine similarity, best first)."""
         eng, ix = self._need_engine(), self.index
         q = torch.as_tensor(self.embedder.embed_query(query_text), dtype=torch.float32).reshape(1, -1)
         q = q / q.norm(dim=1, keepdim=True).clamp_min(1e-30)
-        k = min(self._fetch(limit, collection), 228, len(ix.rows))
-        ids, sc, cnt, _ = eng.dense_topk(q.to(torch.bfloat16).to(eng.device), k)
+        k = min(limit, 228, len(ix.rows))
+        ids, sc, cnt, _ = eng.dense_topk(q.to(torch.bfloat16).to(eng.device), k, want=ix.want(collection))  # inside K1
         eng.sync()
         n = int(cnt[0])
-        ids, sc = ids[0, :n].tolist(), sc[0, :n].tolist()
-        score_of = dict(zip(ids, sc))
-        return [ix.row_dict(i, similarity=score_of[i]) for i in self._filter_collection(ids, collection, limit)]
+        return [ix.row_dict(i, similarity=v) for i, v in zip(ids[0, :n].tolist(), sc[0, :n].tolist())]
 
     async def _graph_search(self, cypher: str, keywords: List[str], collection: Optional[str],
                             limit: int) -> List[Dict[str, Any]]:
@@ -426,10 +434,11 @@ class GpuRAG2Retriever:
     # ---- batched entry (new) ----------------------------------------------------------------------
     def retrieve_batch(self, queries: Sequence[str], query_vectors: torch.Tensor,
                        keywords: Sequence[Sequence[str]], graph_ids: Optional[Sequence[Sequence[str]]] = None,
-                       top_k: int = 100, k_sem: int = 100, k_lex: int = 50, weights: Optional[Dict[str, float]] = None
-                       ) -> List[List[RetrievalCandidate]]:
+                       top_k: int = 100, k_sem: int = 100, k_lex: int = 50, weights: Optional[Dict[str, float]] = None,
+                       collections: Optional[Sequence[Optional[str]]] = None) -> List[List[RetrievalCandidate]]:
         """B queries in one pass of K1 + K2 + K3 (no planner, no rerank): returns per query the fused
-        candidates (rrf_score and channel ranks set), ties by chunk id.  query_vectors [B, D]."""
+        candidates (rrf_score and channel ranks set), ties by chunk id.  query_vectors [B, D].
+        collections: per query, the collection its semantic and lexical hits must belong to (None: any)."""
         from .pipeline import TripleHybridSearcher
         eng, ix = self._need_engine(), self.index
         s = TripleHybridSearcher(eng)
@@ -450,7 +459,11 @@ class GpuRAG2Retriever:
         w = weights or {}
         wt = torch.tensor([[w.get("lexical", 0.7), w.get("semantic", 0.8), w.get("graph", 1.0)]] * B,
                           dtype=torch.float64, device=eng.device)
-        out = s.search(Q, qt, qo, g, weights=wt, k_sem=min(k_sem, len(ix.rows)), k_lex=k_lex, top_k=top_k)
+        want = None
+        if collections is not None and any(c is not None for c in collections):
+            want = torch.tensor([-1 if c is None else ix.tag_of.get(c, 0xfffe) for c in collections], dtype=torch.int32,
+                                device=eng.device)
+        out = s.search(Q, qt, qo, g, weights=wt, k_sem=min(k_sem, len(ix.rows)), k_lex=k_lex, top_k=top_k, want=want)
         eng.sync()
         ids, rrf, rk, cnt = out.ids.tolist(), out.rrf.tolist(), out.ranks.tolist(), out.count.tolist()
         res = []
