@@ -156,7 +156,7 @@ int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, i
                   int64_t* out_ids, float* out_scores, int32_t* out_count, void* stream);
 
 /* Tag filter of the lexical channel (the `collection` predicate of rag2_lexical_search, :368-370): same
- * contract as thr_dense_tags_set / thr_dense_topk_tagged; tags [n_docs] uint16 on the device. */
+ * contract as thr_dense_tags_set / thr_dense_topk_tagged; tags [n_docs] uint16 on the device, 8-byte aligned. */
 int thr_bm25_tags_set(thr_handle* h, const uint16_t* tags);
 int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
                          const int32_t* want, int64_t* out_ids, float* out_scores, int32_t* out_count,

@@ -422,12 +422,23 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
           if (m > tau_u) {
             uint32_t z[4] = {0u, 0u, 0u, 0u};
             const uint32_t doc = dz + ((uint32_t)j * kSpanThreads + (uint32_t)tid) * 4u;
+            // A doc outside the query's tag is dropped here: it never enters the list, so tau is learnt from
+            // eligible docs only and the result is the exact top-k of the filtered corpus.  One 8-byte load brings
+            // the tags of all four slots (doc is a multiple of 4).
+            int tg[4] = {want, want, want, want};
+            if (want >= 0) {
+              if ((int64_t)doc + 4 <= a.n_docs) {
+                const ushort4 t4 = __ldg((const ushort4*)(a.tags + doc));
+                tg[0] = t4.x; tg[1] = t4.y; tg[2] = t4.z; tg[3] = t4.w;
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tg[c] = (int64_t)doc + c < a.n_docs ? (int)a.tags[doc + c] : -1;
+              }
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float x = __uint_as_float(v[c]);
-              // a doc outside the query's tag is dropped here: it never enters the list, so tau is learnt from
-              // eligible docs only and the result is the exact top-k of the filtered corpus
-              if (x > tau && (want < 0 || (int)a.tags[doc + c] == want)) {
+              if (x > tau && tg[c] == want) {
                 const int pos = atomicAdd(&s_int[2], 1);
                 if (pos < kSpanCap) cand[pos] = pack_key(x, doc + c);
                 else { *v_ovf = 1; z[c] = v[c]; }              // stays in the accumulator for the next scan
@@ -443,7 +454,10 @@ __global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel
         bar_group<kSpanThreads, kSpanBar>();
         const int n = min(*v_cnt, kSpanCap);
         const bool ovf = *v_ovf != 0;
-        if (!ovf && n <= kSpanCap / 2) break;                 // uniform: the counters are stable here
+        // Under a tag filter every doc above tau costs a tag load whether it is eligible or not, so tau has to
+        // follow the eligible docs closely: compact as soon as the list holds a few more than k entries.
+        const int limit = want >= 0 ? min(kSpanCap / 2, max(2 * a.k, 256)) : kSpanCap / 2;
+        if (!ovf && n <= limit) break;                        // uniform: the counters are stable here
         bar_group<kSpanThreads, kSpanBar>();                  // everyone has read them
         if (n > a.k) compact(n);
         else if (tid == 0) s_int[3] = 0;                      // (cannot overflow with n <= k; keep the flag sane)
@@ -691,6 +705,7 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
 int thr_bm25_tags_set(thr_handle* h, const uint16_t* tags) {
   if (!h) return THR_EINVAL;
   if (!h->bm25) return thr_fail(h, THR_ENOINDEX, "thr_bm25_tags_set: call thr_bm25_index_set first");
+  THR_REQUIRE(h, ((uintptr_t)tags & 7u) == 0, "thr_bm25_tags_set: tags must be 8-byte aligned");
   h->bm25->tags = tags;
   return THR_OK;
 }
