@@ -399,7 +399,7 @@ def main():
         "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": make_config(args, world),
+        "config": {**make_config(args, world), "exchange": searcher.exchange_mode},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clk,

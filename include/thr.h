@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 5
+#define THR_ABI_VERSION 6
 
 enum {
   THR_OK = 0,
@@ -256,6 +256,24 @@ int thr_exchange_pack(thr_handle* h, const int64_t* d_ids, const double* d_sc, c
 int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_sem, int k_lex,
                        int64_t* d_ids, double* d_sc, int32_t* d_cnt, int64_t* l_ids, float* l_sc,
                        int32_t* l_cnt, void* stream);
+
+/* The same exchange over peer memory, without a collective call: thr_exchange_push packs this rank's message
+ * and stores it straight into slot `rank` of EVERY rank's gathered buffer (peer_bufs [G] device array of the
+ * ranks' buffer bases in this process' address space, e.g. torch symmetric memory; + buf_off bytes), then raises
+ * this rank's entry of every rank's signal array (peer_signals [G] bases + sig_off bytes, uint64 [G], zero
+ * before the first step) to `seq` with release semantics at system scope.  done_counter: a zero-initialised
+ * uint32 on the device, owned by the caller.  thr_exchange_merge_pushed is thr_exchange_merge that first waits
+ * (acquire, bounded by the 2 s watchdog -> THR_ETIMEOUT) until signals[g] >= seq for every g.  seq grows by one
+ * per step; alternate two buffer halves (buf_off) between consecutive steps so that a fast rank's next push
+ * cannot overwrite a message a slow rank is still merging.
+ */
+int thr_exchange_push(thr_handle* h, const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,
+                      const int64_t* l_ids, const float* l_sc, const int32_t* l_cnt, int B, int k_sem,
+                      int k_lex, void* const* peer_bufs, int64_t buf_off, uint64_t* const* peer_signals,
+                      int64_t sig_off, int rank, int G, uint64_t seq, uint32_t* done_counter, void* stream);
+int thr_exchange_merge_pushed(thr_handle* h, const void* gathered, const uint64_t* signals, uint64_t seq,
+                              int G, int B, int k_sem, int k_lex, int64_t* d_ids, double* d_sc,
+                              int32_t* d_cnt, int64_t* l_ids, float* l_sc, int32_t* l_cnt, void* stream);
 
 #ifdef __cplusplus
 }

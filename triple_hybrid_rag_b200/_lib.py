@@ -17,7 +17,7 @@ THR_EINVAL, THR_ECUDA, THR_EUNSUPPORTED, THR_ENOINDEX, THR_EOVERFLOW, THR_ETIMEO
     -1, -2, -3, -4, -5, -6, -7)
 FUSE_RAG2, FUSE_LIB, FUSE_RAG1 = 0, 1, 2
 TIE_INSERTION, TIE_CHUNK_ID = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 PROF_SLOTS = ("dense_score", "dense_finalize", "bm25", "fuse", "maxsim", "merge", "safety", "bm25_prep", "dense_seed")
 
 _p, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -50,6 +50,8 @@ SIGNATURES = {
     "thr_exchange_msg_bytes": (_i64, [_i, _i, _i]),
     "thr_exchange_pack": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "thr_exchange_merge": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "thr_exchange_push": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, C.c_uint64, _p, _p]),
+    "thr_exchange_merge_pushed": (_i, [_p, _p, _p, C.c_uint64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

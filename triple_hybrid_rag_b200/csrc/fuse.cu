@@ -489,17 +489,80 @@ __global__ void __launch_bounds__(256) exchange_pack_kernel(const int64_t* d_ids
   }
 }
 
+// The same message, but PUSHED: every element is stored straight into slot `rank` of every rank's gathered buffer
+// (peer stores over NVLink into symmetric memory; the own buffer is one of the G destinations), and the last CTA
+// to finish raises this rank's sequence number in every rank's signal array.  Pack, transfer and notification are
+// one kernel; no collective call, no copy engine.  `done` is a zero-initialised device counter.
+__global__ void __launch_bounds__(256) exchange_push_kernel(const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,
+                                                            const int64_t* l_ids, const float* l_sc, const int32_t* l_cnt,
+                                                            int B, int k_sem, int k_lex, int k,
+                                                            uint8_t* const* peer_bufs, size_t slot_off,
+                                                            unsigned long long* const* peer_sig, size_t sig_off, int rank,
+                                                            int G, unsigned long long seq, unsigned int* done) {
+  const size_t n = (size_t)2 * B * k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % k);
+    const int row = (int)(i / k);
+    double s = -INFINITY;
+    int64_t id = -1;
+    if (row < B) {
+      if (j < k_sem) { s = d_sc[(size_t)row * k_sem + j]; id = d_ids[(size_t)row * k_sem + j]; }
+    } else if (j < k_lex) {
+      s = (double)l_sc[(size_t)(row - B) * k_lex + j];
+      id = l_ids[(size_t)(row - B) * k_lex + j];
+    }
+    const int32_t c = j == 0 ? (row < B ? d_cnt[row] : l_cnt[row - B]) : 0;
+    for (int g = 0; g < G; ++g) {
+      uint8_t* msg = peer_bufs[g] + slot_off;
+      ((double*)msg)[i] = s;
+      ((int64_t*)(msg + n * 8))[i] = id;
+      if (j == 0) ((int32_t*)(msg + 2 * n * 8))[row] = c;
+    }
+  }
+  __threadfence_system();   // this thread's peer stores are performed before the CTA counts itself done
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {   // last CTA: every CTA's stores are visible system-wide (fence cumulativity)
+      *done = 0u;
+      __threadfence_system();
+      for (int g = 0; g < G; ++g) {
+        unsigned long long* p = (unsigned long long*)((uint8_t*)peer_sig[g] + sig_off) + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(seq) : "memory");
+      }
+    }
+  }
+}
+
 // One CTA per (channel, query): merge the G lists out of the gathered messages, write the channel's final list in
 // the channel's own output format (semantic: f64 scores, -inf padding; lexical: f32 scores, 0 padding as
 // thr_bm25_topk writes them).
+// sig != nullptr (pushed messages): sig[g] >= seq says rank g's message of this step has landed in `gathered`.
 __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gathered, size_t msg_bytes, int G, int B,
                                                              int k_sem, int k_lex, int k, int64_t* d_ids, double* d_sc,
                                                              int32_t* d_cnt, int64_t* l_ids, float* l_sc,
-                                                             int32_t* l_cnt) {
+                                                             int32_t* l_cnt, const unsigned long long* sig,
+                                                             unsigned long long seq, thr_dev_status* status) {
   __shared__ double s_sc[kMergeMax];
   __shared__ int64_t s_id[kMergeMax];
   __shared__ int s_total;
   const int row = blockIdx.x, tid = threadIdx.x;
+  if (sig) {
+    if (tid < G) {   // bounded wait: a rank that never arrives surfaces as THR_ETIMEOUT, not as a hung GPU
+      uint64_t t0 = 0;
+      for (uint32_t spin = 1;; ++spin) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(sig + tid) : "memory");
+        if (v >= seq) break;
+        if ((spin & 1023u) == 0) {
+          const uint64_t now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > THR_WATCHDOG_NS) { dev_report(status, THR_ETIMEOUT, 520, (long long)tid); __trap(); }
+        }
+      }
+    }
+    __syncthreads();
+  }
   const int n = G * k;
   const size_t nrow = (size_t)2 * B * k;
   int P = 32;
@@ -513,10 +576,10 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gath
     if (i < n) {
       const int g = i / k, j = i % k;
       const uint8_t* m = gathered + (size_t)g * msg_bytes;
-      const int cnt = ((const int32_t*)(m + 2 * nrow * 8))[row];
+      const int cnt = __ldcg((const int32_t*)(m + 2 * nrow * 8) + row);   // L2 is the point of coherence for peer stores
       if (j < cnt) {
-        s = ((const double*)m)[(size_t)row * k + j];
-        id = ((const int64_t*)(m + nrow * 8))[(size_t)row * k + j];
+        s = __ldcg((const double*)m + (size_t)row * k + j);
+        id = (int64_t)__ldcg((const long long*)(m + nrow * 8) + (size_t)row * k + j);
         ++local;
       }
     }
@@ -682,11 +745,13 @@ int thr_exchange_pack(thr_handle* h, const int64_t* d_ids, const double* d_sc, c
   return THR_OK;
 }
 
-int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_sem, int k_lex, int64_t* d_ids,
-                       double* d_sc, int32_t* d_cnt, int64_t* l_ids, float* l_sc, int32_t* l_cnt, void* stream) {
+int thr_exchange_merge_pushed(thr_handle* h, const void* gathered, const uint64_t* signals, uint64_t seq, int G, int B,
+                              int k_sem, int k_lex, int64_t* d_ids, double* d_sc, int32_t* d_cnt, int64_t* l_ids,
+                              float* l_sc, int32_t* l_cnt, void* stream) {
   if (!h) return THR_EINVAL;
   cudaSetDevice(h->device);
   THR_REQUIRE(h, G >= 1 && B >= 0 && k_sem >= 1 && k_lex >= 1, "thr_exchange_merge: bad sizes");
+  THR_REQUIRE(h, G <= 256, "thr_exchange_merge: more than 256 ranks");
   if (B == 0) return THR_OK;
   const int k = k_sem > k_lex ? k_sem : k_lex;
   THR_REQUIRE(h, (int64_t)G * k <= kMergeMax, "thr_exchange_merge: G*k = %lld exceeds %d", (long long)G * k, kMergeMax);
@@ -696,9 +761,42 @@ int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_
   const int tok = thr_prof_begin(h, THR_PROF_MERGE, (cudaStream_t)stream);
   exchange_merge_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)gathered,
                                                                  (size_t)thr_exchange_msg_bytes(B, k_sem, k_lex), G, B, k_sem,
-                                                                 k_lex, k, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt);
+                                                                 k_lex, k, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt,
+                                                                 (const unsigned long long*)signals, (unsigned long long)seq,
+                                                                 h->d_status);
   thr_prof_end(h, tok, (cudaStream_t)stream);
   THR_CHECK_LAUNCH(h, "exchange_merge_kernel");
+  return THR_OK;
+}
+
+int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_sem, int k_lex, int64_t* d_ids,
+                       double* d_sc, int32_t* d_cnt, int64_t* l_ids, float* l_sc, int32_t* l_cnt, void* stream) {
+  return thr_exchange_merge_pushed(h, gathered, nullptr, 0, G, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt,
+                                   stream);
+}
+
+int thr_exchange_push(thr_handle* h, const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,
+                      const int64_t* l_ids, const float* l_sc, const int32_t* l_cnt, int B, int k_sem, int k_lex,
+                      void* const* peer_bufs, int64_t buf_off, uint64_t* const* peer_signals, int64_t sig_off, int rank,
+                      int G, uint64_t seq, uint32_t* done_counter, void* stream) {
+  if (!h) return THR_EINVAL;
+  cudaSetDevice(h->device);
+  THR_REQUIRE(h, B >= 0 && k_sem >= 1 && k_lex >= 1 && G >= 1 && rank >= 0 && rank < G, "thr_exchange_push: bad sizes");
+  if (B == 0) return THR_OK;
+  THR_REQUIRE(h, d_ids && d_sc && d_cnt && l_ids && l_sc && l_cnt && peer_bufs && peer_signals && done_counter,
+              "thr_exchange_push: NULL argument");
+  THR_REQUIRE(h, buf_off >= 0 && (buf_off & 7) == 0 && sig_off >= 0 && (sig_off & 7) == 0,
+              "thr_exchange_push: offsets must be non-negative multiples of 8");
+  const int k = k_sem > k_lex ? k_sem : k_lex;
+  const size_t n = (size_t)2 * B * k;
+  const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+  const size_t slot_off = (size_t)buf_off + (size_t)rank * (size_t)thr_exchange_msg_bytes(B, k_sem, k_lex);
+  const int tok = thr_prof_begin(h, THR_PROF_MERGE, (cudaStream_t)stream);
+  exchange_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, B, k_sem, k_lex, k, (uint8_t* const*)peer_bufs, slot_off,
+      (unsigned long long* const*)peer_signals, (size_t)sig_off, rank, G, (unsigned long long)seq, done_counter);
+  thr_prof_end(h, tok, (cudaStream_t)stream);
+  THR_CHECK_LAUNCH(h, "exchange_push_kernel");
   return THR_OK;
 }
 

@@ -286,8 +286,28 @@ class Engine:
                                                 _ptr(l_cnt), B, k_sem, k_lex, _ptr(msg), self._stream()))
         return msg
 
-    def exchange_merge(self, gathered: torch.Tensor, G: int, B: int, k_sem: int, k_lex: int):
-        """All-gathered messages [G, msg bytes] -> (d_ids, d_sc f64, d_cnt, l_ids, l_sc f32, l_cnt), one launch."""
+    def exchange_push(self, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, peer_bufs_dev: int, buf_off: int,
+                      peer_signals_dev: int, sig_off: int, rank: int, G: int, seq: int, done: torch.Tensor):
+        """Pack this rank's lists and store them into slot `rank` of every rank's gathered buffer over peer memory,
+        then raise this rank's sequence number everywhere (include/thr.h: thr_exchange_push).  peer_bufs_dev /
+        peer_signals_dev: device addresses of the [G] pointer arrays (torch symmetric memory's buffer_ptrs_dev /
+        signal_pad_ptrs_dev)."""
+        B, k_sem = d_ids.shape
+        k_lex = l_ids.shape[1]
+        d_ids = self._dev(d_ids, torch.int64, "d_ids"); d_sc = self._dev(d_sc, torch.float64, "d_sc")
+        d_cnt = self._dev(d_cnt, torch.int32, "d_cnt"); l_ids = self._dev(l_ids, torch.int64, "l_ids")
+        l_sc = self._dev(l_sc, torch.float32, "l_sc"); l_cnt = self._dev(l_cnt, torch.int32, "l_cnt")
+        done = self._dev(done, torch.int32, "done")
+        self._check(self._lib.thr_exchange_push(self._h, _ptr(d_ids), _ptr(d_sc), _ptr(d_cnt), _ptr(l_ids), _ptr(l_sc),
+                                                _ptr(l_cnt), B, k_sem, k_lex, C.c_void_p(peer_bufs_dev), buf_off,
+                                                C.c_void_p(peer_signals_dev), sig_off, rank, G, seq, _ptr(done),
+                                                self._stream()))
+
+    def exchange_merge(self, gathered: torch.Tensor, G: int, B: int, k_sem: int, k_lex: int,
+                       signals_ptr: Optional[int] = None, seq: int = 0):
+        """Gathered messages [G, msg bytes] -> (d_ids, d_sc f64, d_cnt, l_ids, l_sc f32, l_cnt), one launch.
+        signals_ptr / seq: for pushed messages, the device address of this rank's signal array and the step's
+        sequence number the kernel waits for (thr_exchange_merge_pushed)."""
         gathered = self._dev(gathered, torch.uint8, "gathered")
         if gathered.numel() != G * self.exchange_msg_bytes(B, k_sem, k_lex):
             raise ValueError("exchange_merge: gathered has the wrong size")
@@ -298,7 +318,9 @@ class Engine:
         l_ids = torch.empty((B, k_lex), dtype=torch.int64, device=dev)
         l_sc = torch.empty((B, k_lex), dtype=torch.float32, device=dev)
         l_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
-        self._check(self._lib.thr_exchange_merge(self._h, _ptr(gathered), G, B, k_sem, k_lex, _ptr(d_ids), _ptr(d_sc),
-                                                 _ptr(d_cnt), _ptr(l_ids), _ptr(l_sc), _ptr(l_cnt), self._stream()))
+        sig = None if signals_ptr is None else C.c_void_p(signals_ptr)
+        self._check(self._lib.thr_exchange_merge_pushed(self._h, _ptr(gathered), sig, seq, G, B, k_sem, k_lex, _ptr(d_ids),
+                                                        _ptr(d_sc), _ptr(d_cnt), _ptr(l_ids), _ptr(l_sc), _ptr(l_cnt),
+                                                        self._stream()))
         return d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt
 

@@ -16,6 +16,8 @@ merged lists and runs the fusion redundantly (no second exchange).
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Optional
 
@@ -88,10 +90,13 @@ class SearchOutput:
 
 
 class TripleHybridSearcher:
-    def __init__(self, engine: Engine, group=None):
-        """group: a torch.distributed process group (NCCL) when the corpus is sharded, else None."""
+    def __init__(self, engine: Engine, group=None, exchange: Optional[str] = None):
+        """group: a torch.distributed process group (NCCL) when the corpus is sharded, else None.
+        exchange: "peer" (pushed over peer memory when it can be set up, the default) or "nccl" (always the
+        all-gather); the environment variable THR_EXCHANGE sets the default."""
         self.engine = engine
         self.group = group
+        self.exchange = exchange or os.environ.get("THR_EXCHANGE", "peer")
         self.world = 1
         self.rank = 0
         if group is not None:
@@ -102,6 +107,7 @@ class TripleHybridSearcher:
         self.has_bm25 = False
         self._pinned = {}
         self._offs = {}
+        self.exchange_fallback = None   # why the pushed exchange is not in use (None: it is, or world == 1)
 
     # ---- index residency -------------------------------------------------------------------
     def set_dense(self, X_local: torch.Tensor, id_base: int = 0):
@@ -159,12 +165,64 @@ class TripleHybridSearcher:
             self._offs[key] = off
         return (ids.reshape(-1), off, None)
 
+    # Signal arrays live in the last KiB of torch symmetric memory's signal pad (its own barriers use the front).
+    _SIG_OFF = 8192
+
+    def _peer_state(self, B, k_sem, k_lex):
+        """Symmetric-memory buffers for the pushed exchange of this (B, k_sem, k_lex): two halves of G message
+        slots, mapped into every rank.  None when symmetric memory cannot be set up (then: NCCL all-gather)."""
+        key = ("peer", B, k_sem, k_lex)
+        st = self._offs.get(key)
+        if st is not None or key in self._offs:
+            return st
+        st = None
+        if self.exchange != "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                eng = self.engine
+                nbytes = eng.exchange_msg_bytes(B, k_sem, k_lex)
+                buf = symm.empty(2 * self.world * nbytes, dtype=torch.uint8, device=eng.device)
+                hdl = symm.rendezvous(buf, self.group)
+                if hdl.signal_pad_size < self._SIG_OFF + 8 * self.world:
+                    raise RuntimeError("signal pad too small")
+                st = {"buf": buf, "hdl": hdl, "nbytes": nbytes, "seq": 0,
+                      "done": torch.zeros((1,), dtype=torch.int32, device=eng.device),
+                      "sig_ptr": int(hdl.signal_pad_ptrs[self.rank]) + self._SIG_OFF}
+                hdl.barrier()   # every rank's buffers and signal pads exist and are zero before the first push
+            except Exception as e:  # no peer mapping on this system: the collective is NCCL's
+                self.exchange_fallback = f"{type(e).__name__}: {e}"
+                st = None
+        else:
+            self.exchange_fallback = "exchange='nccl' requested"
+        self._offs[key] = st
+        return st
+
+    @property
+    def exchange_mode(self) -> str:
+        if self.world == 1:
+            return "none (single GPU)"
+        if any(isinstance(k, tuple) and k and k[0] == "peer" and v is not None for k, v in self._offs.items()):
+            return "pushed over NVLink peer memory (torch symmetric memory buffers, thr_exchange_push)"
+        return f"NCCL all-gather ({self.exchange_fallback})"
+
     def _exchange(self, B, k_sem, k_lex, d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt):
-        """The exchange step on the GPU: pack (one launch) -> ONE NCCL all-gather -> merge of both channels (one
-        launch).  Same message layout and ordering as exchange_topk above, which states it with torch ops and is
-        what the gloo test drives; tests/test_gpu_edges.py checks the two against each other."""
+        """The exchange step on the GPU.  Preferred: thr_exchange_push stores this rank's message straight into every
+        rank's gathered buffer over NVLink peer memory and signals; thr_exchange_merge_pushed waits for the G
+        signals and merges both channels — two launches, no collective call.  Otherwise: pack (one launch) -> ONE
+        NCCL all-gather -> merge (one launch).  Same message layout and ordering as exchange_topk above, which
+        states it with torch ops and is what the gloo test drives; tests/test_gpu_edges.py checks the kernels
+        against it."""
         import torch.distributed as dist
         eng = self.engine
+        st = self._peer_state(B, k_sem, k_lex)
+        if st is not None:
+            st["seq"] += 1
+            half = (st["seq"] & 1) * self.world * st["nbytes"]
+            hdl = st["hdl"]
+            eng.exchange_push(d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, int(hdl.buffer_ptrs_dev), half,
+                              int(hdl.signal_pad_ptrs_dev), self._SIG_OFF, self.rank, self.world, st["seq"], st["done"])
+            mine = st["buf"][half: half + self.world * st["nbytes"]]
+            return eng.exchange_merge(mine, self.world, B, k_sem, k_lex, signals_ptr=st["sig_ptr"], seq=st["seq"])
         nbytes = eng.exchange_msg_bytes(B, k_sem, k_lex)
         msg = torch.empty((nbytes,), dtype=torch.uint8, device=eng.device)
         eng.exchange_pack(d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, msg)
