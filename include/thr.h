@@ -137,7 +137,7 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
  *   skip [V*n_blk + 1] int64: postings[skip[t*n_blk + r] .. skip[t*n_blk + r + 1]) are term t's
  *   postings inside range r (so skip[t*n_blk] .. skip[(t+1)*n_blk] is term t's whole list: the
  *   usual CSR indptr is skip[::n_blk]);  idf [V] float.
- * blk_docs must be a power of two in [256, 2048] (one range = one warp's accumulator).  Arrays stay
+ * blk_docs must be a power of two in [256, 2048] (the skip granularity; the kernel accumulates spans of 30720 / blk_docs ranges at a time).  Arrays stay
  * resident (not copied).
  */
 int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,

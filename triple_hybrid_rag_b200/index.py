@@ -3,7 +3,7 @@
 BM25Index builds the inverted index libthr's K2 kernel reads (layout in include/thr.h): postings in
 term-major CSR order (doc ascending inside a term) stored as {uint32 doc, float32 impact}, plus a
 skip table skip[t * n_blk + r] = first posting of term t whose doc lies in doc range r (ranges of
-`blk_docs` docs, at most 2048: one range is one warp's accumulator).  Building is torch plumbing (sort / bincount / cumsum) and runs on whatever device
+`blk_docs` docs, at most 2048: the skip granularity; the kernel accumulates spans of 15 such ranges).  Building is torch plumbing (sort / bincount / cumsum) and runs on whatever device
 the inputs live on; it is the step before the hot path.  The BM25 formula is
 the one oracle/bm25.py states; idf is always computed with numpy on the host so that both sides
 use the same libm.
