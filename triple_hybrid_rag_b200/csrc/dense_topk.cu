@@ -731,7 +731,18 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
   // Seed pass: score a small prefix of the corpus first and start the full pass from its K'-th best
   // score.  Every cluster then filters with a threshold learnt from ~130k chunks from its first tile on
   // (instead of from -inf), which cuts the epilogue's append work and list compactions several-fold.
-  const int64_t seed_rows = (int64_t)n_clusters * kSeedTiles * kTileN;
+  // tiles per cluster in the seed pass (<= kSeedTiles: the uncompacted lists must fit): a longer prefix gives a
+  // tighter threshold but costs its own scoring and a select over n_clusters * tiles * 256 scores per query
+  static int seed_tiles_env = -1;
+  if (seed_tiles_env < 0) {
+    const char* e = getenv("THR_DENSE_SEED_TILES");
+    seed_tiles_env = e ? atoi(e) : 0;
+    if (seed_tiles_env > kSeedTiles) seed_tiles_env = kSeedTiles;
+  }
+  // measured at D = 1536, B = 256 (score + seed, ms): 1.25M rows 0.897 / 0.854 / 0.915 for 1 / 2 / 3 tiles,
+  // 2.5M rows 1.84 / 1.76 / 1.73
+  const int seed_tiles = seed_tiles_env > 0 ? seed_tiles_env : (st->N >= 2000000 ? kSeedTiles : 2);
+  const int64_t seed_rows = (int64_t)n_clusters * seed_tiles * kTileN;
   const char* noseed = getenv("THR_DENSE_NO_SEED");
   if (st->N >= 16 * seed_rows && !(noseed && noseed[0] == '1')) {
     ScoreArgs sa = a;
