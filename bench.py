@@ -157,7 +157,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    state = cpu_baseline(args)
+    # all the host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would otherwise leave the
+    # reference arm on one thread at N > 1
+    state = cpu_baseline(args, threads=len(os.sched_getaffinity(0)))
     ns, cores = state[5], state[6]
     for _ in range(min(args.warmup, 1)):
         cpu_time_step(args, state)
