@@ -256,6 +256,39 @@ def test_retrieve_batch_matches_oracle_fusion(engine):
         assert got == [(x["id"], x["rrf"].hex(), x["ranks"]) for x in rows]
 
 
+def test_coalescing_front_end_equals_direct_batches(engine):
+    """Concurrent single requests through CoalescingFrontEnd come back exactly as one direct retrieve_batch returns
+    them (collections included: the predicate runs inside K1 / K2 per query)."""
+    import functools
+    from triple_hybrid_rag_b200.frontend import CoalescingFrontEnd
+    n, D = 900, 64
+    chunks, emb, parents = _corpus(n, D, seed=6)
+    ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=1024)
+    r = GpuRAG2Retriever(org_id="t", index=ix)
+    g = torch.Generator().manual_seed(4)
+    nq = 12
+    Q = torch.randn((nq, D), generator=g)
+    kws = [[f"w{(3 * b) % 40}", f"w{(5 * b + 1) % 90}"] for b in range(nq)]
+    colls = [None, "a", "b"] * 4
+    direct = r.retrieve_batch(["q"] * nq, Q, kws, top_k=30, k_sem=25, k_lex=20, collections=colls)
+
+    def batch_fn(queries, vectors, keywords, graph, collections):
+        return r.retrieve_batch(queries, vectors, keywords, graph_ids=graph, top_k=30, k_sem=25, k_lex=20,
+                                collections=collections)
+
+    async def go():
+        fe = CoalescingFrontEnd(batch_fn, max_batch=8, max_wait_ms=50)
+        out = await asyncio.gather(*[fe.retrieve_candidates("q", Q[b], kws[b], collection=colls[b]) for b in range(nq)])
+        return fe, out
+    fe, out = asyncio.run(go())
+    assert fe.batches == [8, 4]
+    key = lambda lst: [(c.child_id, c.rrf_score.hex(), c.lexical_rank, c.semantic_rank) for c in lst]
+    assert [key(x) for x in out] == [key(x) for x in direct]
+    for b in range(nq):
+        if colls[b] is not None:
+            assert out[b] and all(chunks[ix.id_of[c.child_id]]["collection"] == colls[b] for c in out[b])
+
+
 def test_resident_index_save_load(engine, tmp_path):
     chunks, emb, parents = _corpus(300, 64, seed=8)
     ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=256)
