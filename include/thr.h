@@ -263,7 +263,7 @@ int thr_exchange_merge(thr_handle* h, const void* gathered, int G, int B, int k_
  * this rank's entry of every rank's signal array (peer_signals [G] bases + sig_off bytes, uint64 [G], zero
  * before the first step) to `seq` with release semantics at system scope.  done_counter: a zero-initialised
  * uint32 on the device, owned by the caller.  thr_exchange_merge_pushed is thr_exchange_merge that first waits
- * (acquire, bounded by the 2 s watchdog -> THR_ETIMEOUT) until signals[g] >= seq for every g.  seq grows by one
+ * (acquire, bounded by a 60 s watchdog -> THR_ETIMEOUT) until signals[g] >= seq for every g.  seq grows by one
  * per step; alternate two buffer halves (buf_off) between consecutive steps so that a fast rank's next push
  * cannot overwrite a message a slow rank is still merging.
  */

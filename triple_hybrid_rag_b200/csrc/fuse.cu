@@ -538,6 +538,9 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const int64_t* d_ids
 // the channel's own output format (semantic: f64 scores, -inf padding; lexical: f32 scores, 0 padding as
 // thr_bm25_topk writes them).
 // sig != nullptr (pushed messages): sig[g] >= seq says rank g's message of this step has landed in `gathered`.
+// The wait is for another PROCESS (its host may be late by a page fault, an allocation, a slow first step), so its
+// bound is far longer than the on-chip pipelines' 2 s: a dead peer still surfaces as THR_ETIMEOUT, a slow one does not.
+constexpr unsigned long long kPeerWatchdogNs = 60ull * 1000000000ull;
 __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gathered, size_t msg_bytes, int G, int B,
                                                              int k_sem, int k_lex, int k, int64_t* d_ids, double* d_sc,
                                                              int32_t* d_cnt, int64_t* l_ids, float* l_sc,
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gath
         if ((spin & 1023u) == 0) {
           const uint64_t now = global_timer_ns();
           if (t0 == 0) t0 = now;
-          if (now - t0 > THR_WATCHDOG_NS) { dev_report(status, THR_ETIMEOUT, 520, (long long)tid); __trap(); }
+          if (now - t0 > kPeerWatchdogNs) { dev_report(status, THR_ETIMEOUT, 520, (long long)tid); __trap(); }
         }
       }
     }
