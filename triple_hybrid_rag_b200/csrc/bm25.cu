@@ -80,26 +80,12 @@ __device__ uint64_t block_compact_topk_t(uint64_t* keys, int n, int ksel, uint32
       if (match) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
     }
     bar_group<kNT, kBar>();
-    // Find the digit that holds the want-th largest key: warp 0 walks the 256 bins from the top, 8 bins per lane
-    // plus a warp scan (a single thread walking them costs ~100 dependent shared-memory loads per pass).
+    // Find the digit that holds the want-th largest key (warp 0; common.cuh: radix_find_digit).
     if (tid < 32) {
       const int want = *s_want;
-      int h[8], sum = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { h[i] = (int)hist[255 - 8 * tid - i]; sum += h[i]; }
-      int incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (tid >= d) incl += v;
-      }
-      int cum = incl - sum;
-      if (cum < want && want <= incl) {        // exactly one lane: the keys counted so far total >= want
-        int d = 255 - 8 * tid;
-#pragma unroll
-        for (int i = 0; i < 7; ++i)
-          if (cum + h[i] < want && d == 255 - 8 * tid - i) { cum += h[i]; --d; }
-        *s_want = want - cum;
+      int d, above;
+      if (radix_find_digit(hist, want, tid, &d, &above)) {
+        *s_want = want - above;
         *s_prefix = prefix | ((unsigned long long)d << shift);
       }
     }

@@ -106,6 +106,35 @@ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t idx) {
 __device__ __forceinline__ float key_score(uint64_t key) { return f32_from_orderable((uint32_t)(key >> 32)); }
 __device__ __forceinline__ uint32_t key_index(uint64_t key) { return 0xffffffffu - (uint32_t)key; }
 
+// One step of an MSD radix select over a 256-bin histogram in shared memory, by the first warp of the CTA
+// (tid < 32, all 32 lanes): finds the digit d whose bin holds the want-th largest key, counting from bin 255 down
+// (8 bins per lane + a warp scan instead of one thread walking up to 255 dependent shared-memory loads).
+// Returns true in the one lane that found it, with d and the number of keys in the bins above d.
+__device__ __forceinline__ bool radix_find_digit(const uint32_t* hist, int want, int lane, int* d_out, int* above_out) {
+  int h[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { h[i] = (int)hist[255 - 8 * lane - i]; sum += h[i]; }
+  int incl = sum;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, s);
+    if (lane >= s) incl += v;
+  }
+  int cum = incl - sum;
+  // the lane whose bins contain the want-th key; if the bins hold fewer than `want` keys in total, lane 31 ends
+  // at digit 0 like the serial walk would
+  const bool mine = cum < want && (want <= incl || lane == 31);
+  if (mine) {
+    int d = 255 - 8 * lane;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+      if (cum + h[i] < want && d == 255 - 8 * lane - i) { cum += h[i]; --d; }
+    *d_out = d;
+    *above_out = cum;
+  }
+  return mine;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -437,14 +437,13 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
         if (match) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
       }
       __syncthreads();
-      if (tid == 0) {
-        int want = s_want, cum = 0, d = 255;
-        for (; d > 0; --d) {
-          if (cum + (int)hist[d] >= want) break;
-          cum += hist[d];
+      if (tid < 32) {
+        const int want = s_want;
+        int d, above;
+        if (radix_find_digit(hist, want, tid, &d, &above)) {
+          s_want = want - above;
+          s_prefix = prefix | ((uint64_t)d << shift);
         }
-        s_want = want - cum;
-        s_prefix = prefix | ((uint64_t)d << shift);
       }
       __syncthreads();
     }
