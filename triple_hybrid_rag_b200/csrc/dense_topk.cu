@@ -732,10 +732,9 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
   // (instead of from -inf), which cuts the epilogue's append work and list compactions several-fold.
   // tiles per cluster in the seed pass (<= kSeedTiles: the uncompacted lists must fit): a longer prefix gives a
   // tighter threshold but costs its own scoring and a select over n_clusters * tiles * 256 scores per query
-  static int seed_tiles_env = -1;
-  if (seed_tiles_env < 0) {
-    const char* e = getenv("THR_DENSE_SEED_TILES");
-    seed_tiles_env = e ? atoi(e) : 0;
+  int seed_tiles_env = 0;   // read per call: lets one process compare settings back to back (scripts/seed_probe.py)
+  if (const char* e = getenv("THR_DENSE_SEED_TILES")) {
+    seed_tiles_env = atoi(e);
     if (seed_tiles_env > kSeedTiles) seed_tiles_env = kSeedTiles;
   }
   // measured at D = 1536, B = 256 (score + seed, ms): 1.25M rows 0.897 / 0.854 / 0.915 for 1 / 2 / 3 tiles,
