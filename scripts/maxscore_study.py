@@ -45,3 +45,14 @@ print(f"docs={N} queries={B} k={k}: postings of all terms {tot_post}, of essenti
       f"({100 * ess_post / tot_post:.1f} %), look-ups into non-essential lists {touched_ess} "
       f"({100 * touched_ess / tot_post:.1f} % of the postings)")
 print("per-query essential fraction: p10 %.2f  p50 %.2f  p90 %.2f" % tuple(np.percentile(fr, [10, 50, 90])))
+
+# the same question with a RUNNING tau, as a kernel would have it (oracle/bm25_pruned.py, exactness pinned by
+# tests/test_oracle_bm25_pruned.py): blocks of 32768 docs in ascending id, tau = k-th best so far
+from oracle.bm25_pruned import bm25_topk_pruned
+for budget in (1.0, 0.7, 0.5, 0.3):
+    st = {}
+    gi, gs, gc = bm25_topk_pruned(idx, qs, k, stats=st, ne_budget=budget)
+    assert np.array_equal(gi, ids) and np.array_equal(gs.view(np.uint32), sc.view(np.uint32))
+    print(f"running tau, non-essential budget {budget:.1f} * tau: streamed {100 * st['streamed'] / st['postings']:.1f} % of the "
+          f"postings, survivors re-scored {100 * st['survivors'] / max(st['touched'], 1):.1f} % of the touched docs, "
+          f"look-ups {100 * st['lookups'] / st['postings']:.1f} % of the postings; results identical")
