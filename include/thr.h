@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 6
+#define THR_ABI_VERSION 7
 
 enum {
   THR_OK = 0,
@@ -137,8 +137,9 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
  *   skip [V*n_blk + 1] int64: postings[skip[t*n_blk + r] .. skip[t*n_blk + r + 1]) are term t's
  *   postings inside range r (so skip[t*n_blk] .. skip[(t+1)*n_blk] is term t's whole list: the
  *   usual CSR indptr is skip[::n_blk]);  idf [V] float.
- * blk_docs must be a power of two in [256, 2048] (the skip granularity; the kernel accumulates spans of 30720 / blk_docs ranges at a time).  Arrays stay
- * resident (not copied).
+ * blk_docs must be a power of two in [256, 2048] (the skip granularity: one warp of the kernel owns one range at a
+ * time).  idf must be >= 0 (BM25's ln(1 + ...) always is): the kernel relies on partial sums never decreasing.
+ * Arrays stay resident (not copied).
  */
 int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
                        const float* idf, int64_t n_docs, int32_t n_blk, int32_t blk_docs,
@@ -161,6 +162,16 @@ int thr_bm25_tags_set(thr_handle* h, const uint16_t* tags);
 int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
                          const int32_t* want, int64_t* out_ids, float* out_scores, int32_t* out_count,
                          void* stream);
+
+/* AND semantics — the `tsv @@ plainto_tsquery(...)` predicate of rag2_lexical_search
+ * (database/migrations/20260114_rag2_schema.sql:369: every lexeme of the query must match).  thr_bm25_topk_ex is
+ * thr_bm25_topk_tagged (want may be NULL) with flags: THR_BM25_REQUIRE_ALL keeps only docs that contain EVERY
+ * distinct term of the query (a repeated term counts and scores once; a term id outside [0,V) or without
+ * postings means no doc matches); scores and order are as above, restricted to those docs. */
+enum { THR_BM25_REQUIRE_ALL = 1 };
+int thr_bm25_topk_ex(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                     const int32_t* want, int flags, int64_t* out_ids, float* out_scores, int32_t* out_count,
+                     void* stream);
 
 /* ---- K3: weighted RRF fusion + safety threshold + conformal denoise ---------------
  * Replaces, bit-exactly in fp64:

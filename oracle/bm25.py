@@ -54,11 +54,13 @@ class CsrIndex:
         return CsrIndex(indptr, doc.astype(np.int64), imp, idf.astype(np.float32), n_docs)
 
 
-def bm25_topk(index: CsrIndex, queries: Sequence[Sequence[int]], k: int, id_base: int = 0, tags=None, want=None
-              ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def bm25_topk(index: CsrIndex, queries: Sequence[Sequence[int]], k: int, id_base: int = 0, tags=None, want=None,
+              require_all: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Returns ids [B,k] int64 (-1 padded), scores [B,k] float32, count [B] int32.
     tags [n_docs] / want [B]: the collection predicate of rag2_lexical_search (20260114_rag2_schema.sql:368-370) —
-    query q only sees docs with tags == want[q] (want < 0: all)."""
+    query q only sees docs with tags == want[q] (want < 0: all).
+    require_all: the `tsv @@ plainto_tsquery(...)` predicate (:369) — only docs that contain EVERY distinct term of
+    the query; a repeated term counts and scores once; an unknown term (outside [0,V)) means no doc matches."""
     B = len(queries)
     out_i = np.full((B, k), -1, dtype=np.int64)
     out_s = np.zeros((B, k), dtype=np.float32)
@@ -66,15 +68,26 @@ def bm25_topk(index: CsrIndex, queries: Sequence[Sequence[int]], k: int, id_base
     V = index.indptr.shape[0] - 1
     for qi, terms in enumerate(queries):
         acc = np.zeros(index.n_docs, dtype=np.float32)
+        hits = np.zeros(index.n_docs, dtype=np.int32)
+        need, dead, seen = 0, False, set()
         for t in terms:
             t = int(t)
             if t < 0 or t >= V:
+                dead = True
                 continue
+            if require_all:
+                if t in seen:
+                    continue
+                seen.add(t)
+            need += 1
             lo, hi = index.indptr[t], index.indptr[t + 1]
             d = index.doc[lo:hi]
             contrib = (index.idf[t] * index.imp[lo:hi]).astype(np.float32)  # fp32 multiply
             acc[d] = acc[d] + contrib                                        # fp32 add; docs unique per list
+            hits[d] += 1
         ok = acc > 0
+        if require_all:
+            ok &= (hits == need) & (need > 0) & (not dead)
         if want is not None and int(want[qi]) >= 0:
             ok &= np.asarray(tags) == int(want[qi])
         hit = np.nonzero(ok)[0]

@@ -18,13 +18,13 @@ def _corpus(n_docs, V, blk_docs):
     return idx, orc
 
 
-def _check(engine, idx, orc, queries, k, id_base=0):
+def _check(engine, idx, orc, queries, k, id_base=0, require_all=False):
     d = idx.to(engine.device)
     engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
     qt, qo = pack_queries(queries, engine.device)
-    ids, sc, cnt = engine.bm25_topk(qt, qo, k)
+    ids, sc, cnt = engine.bm25_topk(qt, qo, k, require_all=require_all)
     engine.sync()
-    wi, ws, wc = ob.bm25_topk(orc, queries, k, id_base=id_base)
+    wi, ws, wc = ob.bm25_topk(orc, queries, k, id_base=id_base, require_all=require_all)
     ids, sc, cnt = ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
     assert np.array_equal(cnt, wc)
     assert np.array_equal(ids, wi), f"{(ids != wi).sum()} of {ids.size} ids differ"
@@ -46,6 +46,30 @@ def test_bm25_heavy_terms_split_stages_and_edge_queries(engine):
     qs = [[0, 1, 2, 3, 4, 5, 6, 7], [0], [1999], [], [5000, -3], [10, 10, 11], [3, 700, 1500], list(range(32))]
     _check(engine, idx, orc, qs, 256)
     _check(engine, idx, orc, qs, 1, id_base=123456789)
+
+
+@pytest.mark.parametrize("blk", [256, 2048])
+def test_bm25_and_semantics(engine, blk):
+    """`tsv @@ plainto_tsquery` (20260114_rag2_schema.sql:369): every distinct query term must match.  Frequent
+    terms so that intersections are non-empty; also repeated, unknown and single terms, and k larger than the
+    number of matching docs."""
+    idx, orc = _corpus(30_000, 3_000, blk)
+    qs = [[0, 1], [2, 5, 9], [0, 0, 3], [1, 40, 200], [7], [3, 2999], [4, 5000], [], [10, 11, 12, 13, 14, 15],
+          [0, 1, 2, 3, 4, 5, 6, 7], [100, 300, 20]]
+    for k in (10, 100, 256):
+        _check(engine, idx, orc, qs, k, require_all=True)
+    _check(engine, idx, orc, synth.bm25_queries(32, V=3_000, min_rank=5), 50, require_all=True)
+
+
+def test_bm25_rejects_negative_idf(engine):
+    from triple_hybrid_rag_b200._lib import ThrError
+    idx, _ = _corpus(3_000, 500, 256)
+    d = idx.to(engine.device)
+    bad = d.idf.clone()
+    bad[7] = -1.0
+    with pytest.raises(ThrError, match="idf"):
+        engine.bm25_index_set(d.skip, d.postings, bad, d.n_docs, d.blk_docs, d.V)
+    engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V)
 
 
 def test_bm25_fp32_within_tolerance_of_fp64(engine):

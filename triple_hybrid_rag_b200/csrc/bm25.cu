@@ -12,17 +12,36 @@
 // a term) and skip[t * n_blk + r] = first posting of term t whose doc lies in range r (blk_docs docs).
 //
 // Launch sequence of thr_bm25_topk: cost per query -> plan (cut queries into units = doc-range slices of
-// about equal cost) -> order (heaviest first) -> bm25_span_kernel (one unit at a time per CTA, fetched
+// about equal cost) -> order (heaviest first) -> bm25_range_kernel (one unit at a time per CTA, fetched
 // dynamically; writes each unit's sorted top-k) -> bm25_merge_kernel (per query, merge its units' lists).
-// The kernel is bound by instruction issue and latency, not by DRAM: a query touches ~13% of the docs, so
-// what counts is the number of (term, span) visits and the instructions each visit costs.
+//
+// bm25_range_kernel (round 2; DESIGN.md §4/§8 has the measurements that led here).  The round-1 kernel let a
+// CTA own a 30720-doc accumulator and sent every consumer warp through every chunk of postings: ~970 M warp
+// instructions per 10M-doc batch, most of them barrier/poll/scan overhead.  Here a WARP owns one skip range
+// (blk_docs docs, one fp32 slot per doc in shared memory) at a time and nothing is shared between warps on
+// the hot path:
+//   * lane t <-> query term t loads the range's two skip entries; a term's postings inside the range are one
+//     contiguous piece, read straight from global memory (coalesced 8-byte loads, kDepth chunks of 32 in
+//     flight per warp, L2 prefetch two ranges ahead) — no staging ring, no mbarriers, no producer warp;
+//   * terms are added in query order by the owning warp (docs of one term are distinct: no atomics; only
+//     __syncwarp between chunks), so the fp32 sum is the definition's;
+//   * there is no scan of the accumulator: an add that takes a slot across the running threshold tau
+//     (old <= tau < new; contributions are >= 0, so exactly one add per qualifying doc does) remembers the doc in
+//     a register, the final scores of those docs are read back after the last term, and the range is cleared
+//     with 16-byte stores.  A lane that crosses twice in one range, or tau == 0, falls back to scanning the
+//     warp's own slots (the warm-up of a unit, and queries with fewer than k hits);
+//   * candidates go to a per-warp list in global memory (appends are rare once tau has converged); tau is
+//     shared per CTA and tracked by a 256-bin histogram of candidate scores (a warp walks it after it
+//     appended: the k-th best candidate's bin edge is a lower bound of the final k-th score), exact
+//     warp-level sort-select only when a list stays long after filtering (massive ties); units of one query on
+//     different CTAs exchange tau through one global word.
 #include <math_constants.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kMaxTerms = 32;                    // lanes of the producer warp: one per query term
+constexpr int kMaxTerms = 32;                    // lanes of a warp: one per query term
 constexpr int kMaxBlkDocs = 2048;                // largest skip range
 constexpr int kMaxSelB = 256;                    // largest k
 
@@ -49,6 +68,10 @@ struct Bm25Args {
   int32_t* part_cnt;      // [max_units]
   const uint16_t* tags;   // [n_docs] nullable: per-doc tag (collection id) for filtered queries
   const int32_t* want;    // [B] nullable: tag a query's docs must carry, < 0 = any
+  uint64_t* wlists;       // [grid][warps][kListCap] per-warp candidate lists
+  unsigned* tau_q;        // [B] running threshold per query (fp32 bits of a score >= 0), shared by its units
+  int require_all;        // AND semantics: a doc must contain every (distinct, known) query term
+  int pf_dist;            // L2 prefetch distance in ranges (0: none)
   thr_dev_status* status;
 };
 
@@ -57,448 +80,536 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// Barrier among the first kNT threads of the CTA (named barrier kBar; kBar 0 with kNT = blockDim is __syncthreads).
-template <int kNT, int kBar>
-__device__ __forceinline__ void bar_group() {
-  asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kNT) : "memory");
-}
-
-// Cooperative among kNT threads: keep the ksel largest of keys[0..n) in place, n > ksel, n <= kCap.
-// Returns the ksel-th largest key.  hist/scal are shared scratch.
-template <int kNT, int kCap, int kBar>
-__device__ uint64_t block_compact_topk_t(uint64_t* keys, int n, int ksel, uint32_t* hist,
-                                         unsigned long long* s_prefix, int* s_want, int* s_cnt, int tid) {
-  if (tid == 0) { *s_prefix = 0ull; *s_want = ksel; }
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = 56 - 8 * pass;
-    for (int i = tid; i < 256; i += kNT) hist[i] = 0;
-    bar_group<kNT, kBar>();
-    const uint64_t prefix = *s_prefix;
-    for (int i = tid; i < n; i += kNT) {
-      const uint64_t key = keys[i];
-      const bool match = pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8));
-      if (match) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
-    }
-    bar_group<kNT, kBar>();
-    // Find the digit that holds the want-th largest key (warp 0; common.cuh: radix_find_digit).
-    if (tid < 32) {
-      const int want = *s_want;
-      int d, above;
-      if (radix_find_digit(hist, want, tid, &d, &above)) {
-        *s_want = want - above;
-        *s_prefix = prefix | ((unsigned long long)d << shift);
-      }
-    }
-    bar_group<kNT, kBar>();
-  }
-  const uint64_t T = *s_prefix;
-  // survivors: read everything first, then rewrite the front
-  constexpr int kPer = (kCap + kNT - 1) / kNT;
-  uint64_t mine[kPer];
-#pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    int i = tid + j * kNT;
-    mine[j] = i < n ? keys[i] : 0ull;
-  }
-  if (tid == 0) *s_cnt = 0;
-  bar_group<kNT, kBar>();
-#pragma unroll
-  for (int j = 0; j < kPer; ++j)
-    if (mine[j] >= T && mine[j] != 0ull) keys[atomicAdd(s_cnt, 1)] = mine[j];
-  bar_group<kNT, kBar>();
-  return T;
-}
 // ------------------------------------------------------------------------------------------------
-// The CTA owns the accumulator.
-//
-// A span is kSpanDocs consecutive docs (a whole number of skip ranges) with one fp32 accumulator slot per doc
-// in shared memory.  A term's postings inside a span are ONE contiguous piece of the term-major posting array
-// (skip[t][first range] .. skip[t][last range + 1]), so the producer warp streams it into a ring of kChunk-posting
-// stages with cp.async.bulk, one descriptor per chunk; all per-(term, span) bookkeeping lives in that one warp.
-// The kSpanThreads consumer threads do nothing but: wait for a chunk, add its postings (<= 2 per thread, docs of
-// one term are distinct: no atomics), release the stage.  Terms are separated by a named barrier (fp32 adds in
-// query order: the sum is part of the definition); after the span's last chunk the accumulator is scanned
-// with 16-byte loads: nonzero slots are zeroed and scores above tau are appended to the candidate list.
-// An append that does not fit leaves its slot in place and raises a flag; the list is then compacted (which raises
-// tau) and the scan repeats, so no threshold warm-up is needed for correctness.
-//
-// Shape (measured at 10M docs, batch 256; the THR_SPAN_* macros exist for such sweeps, scripts/build_variant.sh):
-// time is (number of chunk visits) x (consumer warps) x (instructions per visit) at an IPC of ~1.7, so the span is
-// as large as shared memory allows (fewer visits) and the common path of a visit is ~25 instructions; more
-// warps hide more latency even though most of them have no posting in most chunks (a chunk holds a few hundred):
-//   8 warps x 32k docs 3.36 ms | 16 x 32k 2.28 | 24 x 30k 2.18 | 2 CTAs x 8 warps x 16k 2.76 | 3 x 4 x 12k 3.15.
-#ifndef THR_SPAN_DOCS
-#define THR_SPAN_DOCS 30720
+constexpr int kListCap = 1024;       // entries of a warp's candidate list (global memory)
+constexpr int kListHigh = 512;       // compaction watermark after a range in crossing mode
+constexpr int kListRoom = 384;       // a compaction leaves at most this many entries (>= kMaxSelB)
+constexpr int kDepth = 4;            // posting chunks (32 postings each) in flight per warp
+#ifndef THR_BM25_DESC_CAP
+#define THR_BM25_DESC_CAP 40
 #endif
-#ifndef THR_SPAN_WARPS
-#define THR_SPAN_WARPS 24
+#ifndef THR_BM25_GRAB
+#define THR_BM25_GRAB 4
 #endif
-#ifndef THR_SPAN_CHUNK
-#define THR_SPAN_CHUNK 1536
-#endif
-#ifndef THR_SPAN_STAGES
-#define THR_SPAN_STAGES 6
-#endif
-#ifndef THR_SPAN_CAP
-#define THR_SPAN_CAP 2048
-#endif
-#ifndef THR_SPAN_CTAS
-#define THR_SPAN_CTAS 1
-#endif
-constexpr int kSpanDocs = THR_SPAN_DOCS;          // a multiple of 2048 (every legal blk_docs divides it)
-constexpr int kSpanWarps = THR_SPAN_WARPS;
-constexpr int kSpanThreads = kSpanWarps * 32;     // consumers; warp kSpanWarps is the producer
-constexpr int kChunk = THR_SPAN_CHUNK;            // postings per ring stage
-constexpr int kStages = THR_SPAN_STAGES;
-constexpr int kSpanCap = THR_SPAN_CAP;            // candidate slots
-constexpr int kSpanCtas = THR_SPAN_CTAS;          // CTAs per SM
-constexpr int kSpanBar = 1;                       // named barrier of the consumers
-constexpr int kPerThread = kChunk / kSpanThreads; // postings per consumer thread and chunk
-constexpr int kScanIters = kSpanDocs / (4 * kSpanThreads);
-#ifndef THR_SPAN_ISSUE
-#define THR_SPAN_ISSUE (THR_SPAN_STAGES / 2)
-#endif
-constexpr int kIssue = THR_SPAN_ISSUE;   // chunks the producer issues per round (half the ring)
-constexpr int kScanBatch = kScanIters % 8 == 0 ? 8 : kScanIters % 6 == 0 ? 6 : kScanIters % 4 == 0 ? 4 : 1;
-static_assert(kScanIters % kScanBatch == 0, "scan batches");
-static_assert(kChunk % kSpanThreads == 0 && kChunk % 2 == 0 && kPerThread >= 1 && kPerThread <= 8, "chunk shape");
-static_assert(kSpanDocs % kMaxBlkDocs == 0 && kSpanDocs % (4 * kSpanThreads) == 0, "span shape");
-static_assert(kSpanThreads >= kMaxSelB / 2, "the final sort uses kMaxSelB / 2 threads");
-static_assert(kSpanCap >= 2 * kMaxSelB + 256, "a compaction must free a useful part of the list");
+constexpr int kDescCap = THR_BM25_DESC_CAP;   // piece descriptors per warp (16 B each): >= kMaxTerms + kDepth - 1
+constexpr int kGrab = THR_BM25_GRAB;          // consecutive ranges a warp takes from its unit at a time
+static_assert(kDescCap >= kMaxTerms + kDepth - 1, "a range of a 32-term query must fit the descriptor list");
+constexpr int kHistBins = 256;
+constexpr int kHistShift = 19;                 // 16 bins per octave
+constexpr uint32_t kHistBase = 121u << 4;      // bin 0 starts at 2^-6 (everything smaller lands there too)
+static_assert(kListRoom >= kMaxSelB && kListCap - kListRoom >= 128 + 32, "list head-room");
 
-enum : uint32_t { kFNewUnit = 1u, kFSync = 2u, kFEndSpan = 4u, kFEndUnit = 8u, kFExit = 16u };
+struct RangeShared {
+  uint32_t hist[kHistBins];    // candidate scores of the current unit
+  uint32_t hist2[256];         // radix-select scratch of the unit's final merge
+  unsigned tau_bits;           // the unit's running threshold (bits of a float >= 0)
+  int next_range;
+  int unit;
+  int lock;                    // guards `scratch` during a warp's exact sort-select
+  int n_total;                 // unit end: candidates that survive the final threshold
+  int n_out;
+  int want_sel;
+  unsigned long long prefix;
+};
 
-constexpr size_t kSpanSmem = (size_t)kSpanDocs * 4 + (size_t)kSpanCap * 8 + (size_t)kStages * kChunk * 8 +
-                             kStages * 16 + 2 * kStages * 8 + 256 * 4 + 64 + 256;
-static_assert(kSpanCtas * (kSpanSmem + 1024) <= 233472, "kSpanCtas CTAs per SM");
+__device__ __forceinline__ int tau_bin(uint32_t score_bits) {
+  const int b = (int)(score_bits >> kHistShift) - (int)kHistBase;
+  return min(max(b, 0), kHistBins - 1);
+}
+__device__ __forceinline__ uint32_t key_bits(uint64_t key) { return (uint32_t)(key >> 32) & 0x7fffffffu; }
 
-__global__ void __launch_bounds__(kSpanThreads + 32, kSpanCtas) bm25_span_kernel(const Bm25Args a) {
+// Lower bound of the k-th best candidate score seen by the CTA so far, from the histogram: the lower edge of
+// the bin that holds the k-th best, minus one ulp (so that ties with the edge survive the strict filter).
+// 0 when the histogram holds fewer than k candidates or the k-th lies in the catch-all bin 0.  Warp-collective.
+__device__ __forceinline__ uint32_t hist_tau(const uint32_t* hist, int k, int lane) {
+  int d = 0, above = 0;
+  const bool mine = radix_find_digit(hist, k, lane, &d, &above);
+  uint32_t t = 0;
+  if (mine && d >= 1) t = ((uint32_t)(d + (int)kHistBase) << kHistShift) - 1u;
+  return __reduce_max_sync(0xffffffffu, t);
+}
+
+// Keep the entries whose score is > tau, in place and in order.  Warp-collective; returns the new length.
+__device__ int list_filter(uint64_t* list, int n, uint32_t tau_bits, int lane) {
+  int out = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const uint64_t key = i < n ? __ldcg(list + i) : 0ull;
+    const bool keep = i < n && key_bits(key) > tau_bits;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) __stcg(list + out + __popc(m & ((1u << lane) - 1u)), key);
+    out += __popc(m);
+  }
+  __syncwarp();
+  return out;
+}
+
+// Exact: sort the list (descending keys = score desc, id asc) in the CTA's scratch and keep the k best.
+// Returns the new length; *tau_out = one ulp below the k-th best score (0 if the list is shorter than k).
+__device__ int list_select(uint64_t* list, int n, int k, uint64_t* scratch, int* lock, int lane, uint32_t* tau_out) {
+  if (lane == 0) {
+    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(200);
+  }
+  __syncwarp();
+  int P = 32, lg = 5;
+  while (P < n) { P <<= 1; ++lg; }
+  for (int i = lane; i < P; i += 32) scratch[i] = i < n ? __ldcg(list + i) : 0ull;
+  __syncwarp();
+  for (int ls = 1; ls <= lg; ++ls) {          // size = 1 << ls
+    for (int lt = ls - 1; lt >= 0; --lt) {    // stride = 1 << lt
+      const int stride = 1 << lt;
+      for (int i = lane; i < (P >> 1); i += 32) {
+        const int lo = ((i >> lt) << (lt + 1)) | (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo >> ls) & 1) == 0;
+        const uint64_t x = scratch[lo], y = scratch[hi];
+        if (desc ? (y > x) : (x > y)) { scratch[lo] = y; scratch[hi] = x; }
+      }
+      __syncwarp();
+    }
+  }
+  const int m = min(n, k);
+  for (int i = lane; i < m; i += 32) __stcg(list + i, scratch[i]);
+  *tau_out = n >= k ? key_bits(scratch[k - 1]) - 1u : 0u;
+  __syncwarp();
+  if (lane == 0) { __threadfence_block(); atomicExch(lock, 0); }
+  __syncwarp();
+  return m;
+}
+
+// kAnd: AND semantics (thr_bm25_topk_ex with THR_BM25_REQUIRE_ALL) — a second per-doc array counts the terms that
+// hit the doc; only docs hit by every distinct known term of the query are candidates.
+template <int kBlk, bool kAnd>
+__global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kernel(const Bm25Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* acc = (float*)gen;                                                   // [kSpanDocs]
-  uint64_t* cand = (uint64_t*)(acc + kSpanDocs);                              // [kSpanCap]
-  Posting* ring = (Posting*)(cand + kSpanCap);                               // [kStages][kChunk]
-  uint4* desc = (uint4*)(ring + kStages * kChunk);                            // [kStages]
-  uint64_t* full = (uint64_t*)(desc + kStages);                               // [kStages]
-  uint64_t* empty = full + kStages;                                           // [kStages]
-  uint32_t* hist = (uint32_t*)(empty + kStages);                              // 256
-  unsigned long long* s_prefix = (unsigned long long*)(hist + 256);
-  int* s_int = (int*)(s_prefix + 1);  // [0]=want [1]=cnt(compact) [2]=cand count [3]=overflow
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  float* acc_all = (float*)gen;                                        // [nw][kBlk]
+  uint8_t* hit_all = (uint8_t*)(acc_all + (size_t)nw * kBlk);          // [nw][kBlk] matched-term counts (kAnd)
+  uint64_t* scratch = (uint64_t*)(hit_all + (kAnd ? (size_t)nw * kBlk : 0));   // [kListCap]
+  uint8_t* desc_all = (uint8_t*)(scratch + kListCap);                  // [nw][kDescCap] 16-byte piece descriptors
+  RangeShared* sh = (RangeShared*)(desc_all + (size_t)nw * kDescCap * 16);
+  volatile RangeShared* vsh = sh;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < kSpanDocs; i += kSpanThreads + 32) acc[i] = 0.f;
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), kSpanWarps);
+  for (int i = tid; i < nw * kBlk; i += blockDim.x) acc_all[i] = 0.f;
+  if (kAnd)
+    for (int i = tid; i < nw * kBlk / 4; i += blockDim.x) ((uint32_t*)hit_all)[i] = 0u;
+  for (int i = tid; i < kHistBins; i += blockDim.x) sh->hist[i] = 0u;
+  if (tid == 0) { sh->lock = 0; sh->n_total = 0; sh->n_out = 0; }
+  // Shared-window addresses used on the hot path, made opaque so that the compiler keeps them in registers instead
+  // of re-deriving them from the window base at every use (measured: 34 instructions per range).
+  uint32_t acc_u = smem_u32(acc_all + (size_t)warp * kBlk);            // this warp's accumulator
+  uint32_t hit_u = smem_u32(hit_all + (kAnd ? (size_t)warp * kBlk : 0));
+  uint32_t tau_u = smem_u32(&sh->tau_bits);
+  asm volatile("" : "+r"(acc_u), "+r"(hit_u), "+r"(tau_u));
+  uint64_t* const list = a.wlists + ((size_t)blockIdx.x * nw + warp) * kListCap;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  constexpr int kShift = kBlk == 2048 ? 11 : kBlk == 1024 ? 10 : kBlk == 512 ? 9 : 8;
+  static_assert((1 << kShift) == kBlk, "kBlk must be 256, 512, 1024 or 2048");
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const int w = atomicAdd(a.work_counter, 1);
+      const int u = w < *a.total_units ? a.order[w] : -1;
+      sh->unit = u;
+      if (u >= 0) {
+        sh->next_range = a.units[u].r0;
+        sh->tau_bits = *(volatile unsigned*)&a.tau_q[a.units[u].q];
+      }
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    s_int[2] = 0;
-    s_int[3] = 0;
-  }
-  __syncthreads();
-  const uint32_t ring_u = smem_u32(ring), desc_u = smem_u32(desc), full_u = smem_u32(full), empty_u = smem_u32(empty);
-  const int spr = kSpanDocs / a.blk_docs;   // ranges per span
+    __syncthreads();
+    const int unit = vsh->unit;
+    if (unit < 0) break;
+    const int q = a.units[unit].q, r0 = a.units[unit].r0, r1 = a.units[unit].r1;
+    const int qlo = a.q_off[q];
+    const int nt = min(a.q_off[q + 1] - qlo, kMaxTerms);   // longer queries are reported by bm25_cost_kernel
+    int term = -1;
+    float wgt = 0.f;
+    if (lane < nt) {
+      term = a.q_terms[qlo + lane];
+      if (term < 0 || term >= a.V) term = -1; else wgt = a.idf[term];
+    }
+    int need = 0;      // AND semantics: distinct known terms of the query; an unknown term -> no doc can match
+    bool and_dead = false;
+    if (kAnd) {
+      bool dup = false;
+      for (int u = 0; u < nt; ++u) {
+        const int tu = __shfl_sync(0xffffffffu, term, u);
+        if (u < lane && tu == term) dup = true;
+      }
+      need = __popc(__ballot_sync(0xffffffffu, term >= 0 && !dup));
+      and_dead = __any_sync(0xffffffffu, lane < nt && term < 0) || need == 0;
+      if (dup) term = -1;       // a repeated keyword counts once (plainto_tsquery builds a set of lexemes)
+    }
+    const int want = (a.tags && a.want) ? a.want[q] : -1;
+    const bool any_term = __any_sync(0xffffffffu, term >= 0) && !and_dead;
+    const int64_t* row = a.skip + (size_t)(term < 0 ? 0 : term) * a.n_blk;
+    int n_list = 0;
 
-  if (warp == kSpanWarps) {
-    // ================= producer: lane t <-> query term t =================
-    uint32_t s = 0, ph = 0;
-    auto put = [&](uint32_t x, uint32_t y, uint32_t z, uint32_t w, const Posting* src, uint32_t bytes) {
-      mbar_wait_relaxed(empty_u + s * 8u, ph ^ 1u, a.status, 470);
-      if (lane == 0) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + s * 16u), "r"(x), "r"(y), "r"(z), "r"(w)
-                     : "memory");
-        if (bytes) {
-          mbar_arrive_expect_tx(full_u + s * 8u, bytes);
-          asm volatile(
-              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-              :
-              : "r"(ring_u + s * (uint32_t)(kChunk * 8)), "l"(src), "r"(bytes), "r"(full_u + s * 8u)
-              : "memory");
-        } else {
-          mbar_arrive(full_u + s * 8u);
+    // Walk the histogram, raise the CTA's threshold, tell the query's other units.
+    auto raise_tau = [&]() {
+      const uint32_t tb = hist_tau(sh->hist, a.k, lane);
+      if (lane == 0 && tb > vsh->tau_bits) {
+        atomicMax(&sh->tau_bits, tb);
+        atomicMax(&a.tau_q[q], tb);
+      }
+      __syncwarp();
+    };
+    // Make room in this warp's list: drop what the threshold has overtaken; if the list is still long (ties,
+    // or a threshold that cannot rise because the query has few hits) select its k best exactly.
+    auto compact = [&]() {
+      raise_tau();
+      n_list = list_filter(list, n_list, vsh->tau_bits, lane);
+      if (n_list > kListRoom) {
+        uint32_t tw = 0;
+        n_list = list_select(list, n_list, a.k, scratch, &sh->lock, lane, &tw);
+        if (lane == 0 && tw > vsh->tau_bits) {
+          atomicMax(&sh->tau_bits, tw);
+          atomicMax(&a.tau_q[q], tw);
+        }
+        __syncwarp();
+      }
+    };
+    // Append the lanes' candidates (has) to the list; room for 32 entries is the caller's invariant.
+    auto append = [&](bool has, float score, uint32_t doc) {
+      if (has && want >= 0) has = (int)__ldg(a.tags + doc) == want;
+      const unsigned m = __ballot_sync(0xffffffffu, has);
+      if (m) {
+        if (has) {
+          __stcg(list + n_list + __popc(m & lt_mask), pack_key(score, doc));
+          atomicAdd(&sh->hist[tau_bin(__float_as_uint(score))], 1u);
+        }
+        n_list += __popc(m);
+      }
+    };
+
+    // ---- the unit's posting stream ------------------------------------------------------------------------
+    // Two levels.  build(): lane t <-> query term t turns the next few ranges of the unit into a list of piece
+    // descriptors in shared memory — one per (range, term with postings there), in range then query order:
+    // {pointer to the piece's first posting, postings | kNewRange on a range's first piece, idf} — all terms of a
+    // range at once (ballot + popc give the slots).  A range is padded with empty descriptors to a multiple of
+    // kDepth chunks, so its first chunk always lands in buffer 0 of the pipeline below.
+    // Stream: kDepth chunks of <= 32 postings are in flight in registers; buffer j holds bn[j] postings of one
+    // piece (lane < bn[j] has one), weight bw[j]; an empty chunk (bn = 0) is a no-op for the adds.
+    constexpr int kNewRange = 1 << 16;
+    const uint32_t tb_lo = term >= 0 ? (uint32_t)__ldg(row) : 0u;          // low word of the term's first posting index
+    const Posting* const tp = a.post + (term >= 0 ? __ldg(row) : 0);       // the term's first posting
+    uint4* const desc = (uint4*)(desc_all + (size_t)warp * kDescCap * 16);
+    uint32_t desc_u = smem_u32(desc);
+    asm volatile("" : "+r"(desc_u));
+    const int per_range = __popc(__ballot_sync(0xffffffffu, term >= 0)) + kDepth - 1;   // most descriptors a range takes
+    int np = 0, pend_r = 0, pend_end = 0;
+    auto build = [&]() {
+      np = 0;
+      while (np + per_range <= kDescCap) {
+        if (pend_r >= pend_end) {
+          int r = 0;
+          if (lane == 0) {
+            r = atomicAdd(&sh->next_range, kGrab);
+            const unsigned g = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
+            if (g > vsh->tau_bits) atomicMax(&sh->tau_bits, g);
+          }
+          r = __shfl_sync(0xffffffffu, r, 0);
+          if (r >= r1) break;
+          pend_r = r;
+          pend_end = min(r + kGrab, r1);
+          if (term >= 0 && a.pf_dist > 0) {   // a later grab's postings of this term -> L2 (one contiguous piece)
+            const int f0 = min(r + a.pf_dist, a.n_blk), f1 = min(r + a.pf_dist + kGrab, a.n_blk);
+            const uint32_t o0 = __ldg((const uint32_t*)(row + f0)) - tb_lo, o1 = __ldg((const uint32_t*)(row + f1)) - tb_lo;
+            if (o1 > o0) {
+              const Posting* pb = (const Posting*)((uintptr_t)(tp + o0) & ~(uintptr_t)15);
+              const uint32_t nby = min((uint32_t)((const uint8_t*)(tp + o1) - (const uint8_t*)pb), 32768u);
+              prefetch_l2_bulk(pb, (nby + 15u) & ~15u);
+            }
+          }
+        }
+        uint32_t e[kGrab + 1];   // skip entries of [pend_r, pend_r + kGrab] relative to the term's first posting
+#pragma unroll
+        for (int i = 0; i <= kGrab; ++i)
+          e[i] = term >= 0 ? __ldg((const uint32_t*)(row + min(pend_r + i, a.n_blk))) - tb_lo : 0u;
+#pragma unroll
+        for (int i = 0; i < kGrab; ++i) {
+          if (pend_r < pend_end && np + per_range <= kDescCap) {
+            const int cnt = (int)(e[i + 1] - e[i]);
+            unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+            if (kAnd && __popc(live) < need) live = 0;   // a term without postings here: no doc of the range matches
+            if (live) {
+              const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;
+              const int tot = __reduce_add_sync(0xffffffffu, nch);
+              if (cnt > 0) {
+                const Posting* pp = tp + e[i];
+                const bool first = (live & lt_mask) == 0u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + (uint32_t)(np + __popc(live & lt_mask)) * 16u),
+                             "r"((uint32_t)(uintptr_t)pp), "r"((uint32_t)((uintptr_t)pp >> 32)),
+                             "r"((uint32_t)cnt | (first ? (uint32_t)kNewRange : 0u)), "r"(__float_as_uint(wgt))
+                             : "memory");
+              }
+              np += __popc(live);
+              const int pad = (-tot) & (kDepth - 1);
+              if (lane < pad)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
+              np += pad;
+            }
+            ++pend_r;
+          }
         }
       }
       __syncwarp();
-      if (++s == kStages) { s = 0; ph ^= 1u; }
     };
-    for (;;) {
-      int unit = -1;
-      if (lane == 0) {
-        const int w = atomicAdd(a.work_counter, 1);
-        unit = w < *a.total_units ? a.order[w] : -1;
-      }
-      unit = __shfl_sync(0xffffffffu, unit, 0);
-      if (unit < 0) break;
-      const int q = a.units[unit].q, r0 = a.units[unit].r0, r1 = a.units[unit].r1;
-      const int qlo = a.q_off[q];
-      const int nt = min(a.q_off[q + 1] - qlo, kMaxTerms);   // the host rejects longer queries
-      int term = -1;
-      float wgt = 0.f;
-      if (lane < nt) {
-        term = a.q_terms[qlo + lane];
-        if (term < 0 || term >= a.V) term = -1; else wgt = a.idf[term];
-      }
-      const int64_t* row = a.skip + (size_t)(term < 0 ? 0 : term) * a.n_blk;
-      auto edge = [&](int i) -> int64_t {   // first posting of this lane's term at the start of span i of the unit
-        return term >= 0 ? __ldg(row + min(r0 + i * spr, r1)) : 0;
-      };
-      const int nsp = (r1 - r0 + spr - 1) / spr;
-      int64_t e0 = edge(0), e1 = edge(1), e2 = edge(2), e3 = edge(3);
-      bool first = true;
-      for (int sp = 0; sp < nsp; ++sp) {
-        const int64_t e4 = edge(sp + 4);
-        // the span after the next one -> L2 (the ring then pulls from L2, not DRAM); capped per term
-        if (e3 > e2) {
-          const int64_t b = e2 & ~(int64_t)1;
-          const int64_t nby = min((e3 - b) * 8, (int64_t)32768);
-          prefetch_l2_bulk(a.post + b, (uint32_t)((nby + 15) & ~(int64_t)15));
-        }
-        const int cnt = (int)(e1 - e0);
-        const unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
-        if (live) {
-          const uint32_t doc0 = (uint32_t)(r0 + sp * spr) << a.blk_shift;
-          const int first_live = __ffs(live) - 1;
-          // Chunks of this span, generated lane-parallel.  Term t (lane t) owns nch chunks: the first one ends at a
-          // chunk boundary of the posting array's even-aligned copy grid (m0 postings), the others are whole.
-          const int slack_l = (int)(e0 & 1);
-          const int m0_l = min(cnt, kChunk - slack_l);
-          const int nch = cnt > 0 ? 1 + (cnt - m0_l + kChunk - 1) / kChunk : 0;
-          int incl = nch;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
-          for (int j0 = 0; j0 < total; j0 += kIssue) {      // rounds of kIssue chunks, one chunk per lane
-            const int j = j0 + lane;
-            int t = 0;                                      // term of chunk j = number of terms whose chunks end at or before j
-            for (int u = 0; u < nt; ++u) t += (__shfl_sync(0xffffffffu, incl, u) <= j) ? 1 : 0;
-            t = min(t, 31);
-            const int incl_t = __shfl_sync(0xffffffffu, incl, t);
-            const int nch_t = __shfl_sync(0xffffffffu, nch, t);
-            const int cnt_t = __shfl_sync(0xffffffffu, cnt, t);
-            const int64_t p_t = __shfl_sync(0xffffffffu, (long long)e0, t);
-            const uint32_t w_t = __float_as_uint(__shfl_sync(0xffffffffu, wgt, t));
-            const bool act = lane < kIssue && j < total;
-            if (act) {
-              const int c = j - (incl_t - nch_t);           // chunk index inside the term
-              const int sl_t = (int)(p_t & 1);
-              const int m0 = min(cnt_t, kChunk - sl_t);
-              const int slack = c == 0 ? sl_t : 0;
-              const int64_t p = c == 0 ? p_t : p_t + m0 + (int64_t)(c - 1) * kChunk;
-              const int m = c == 0 ? m0 : min(kChunk, cnt_t - m0 - (c - 1) * kChunk);
-              uint32_t fl = 0;
-              if (first && j == 0) fl |= kFNewUnit;
-              if (c == 0 && t != first_live) fl |= kFSync;
-              if (j == total - 1) fl |= kFEndSpan;
-              uint32_t st = s + (uint32_t)lane, php = ph;
-              if (st >= (uint32_t)kStages) { st -= kStages; php ^= 1u; }
-              mbar_wait(empty_u + st * 8u, php ^ 1u, a.status, 472);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + st * 16u),
-                           "r"((uint32_t)m | ((uint32_t)slack << 16) | (fl << 24)), "r"(w_t), "r"(doc0), "r"((uint32_t)unit)
-                           : "memory");
-              const uint32_t bytes = (uint32_t)((slack + m + 1) & ~1) * 8u;
-              mbar_arrive_expect_tx(full_u + st * 8u, bytes);
-              asm volatile(
-                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                  :
-                  : "r"(ring_u + st * (uint32_t)(kChunk * 8)), "l"(a.post + (p - slack)), "r"(bytes), "r"(full_u + st * 8u)
-                  : "memory");
-            }
-            __syncwarp();
-            s += (uint32_t)min(kIssue, total - j0);
-            if (s >= (uint32_t)kStages) { s -= kStages; ph ^= 1u; }
-          }
-          first = false;
-        }
-        e0 = e1; e1 = e2; e2 = e3; e3 = e4;
-      }
-      put(((first ? kFNewUnit : 0u) | kFEndUnit) << 24, 0u, 0u, (uint32_t)unit, nullptr, 0u);
-    }
-    put(kFExit << 24, 0u, 0u, 0u, nullptr, 0u);
-    return;
+
+    int pi = 0, lrem = 0, flag0 = 0;
+    const Posting* lbase = a.post;   // the piece being streamed, the lane's next posting in it, postings left (<= 0: none)
+    uint32_t loff = 0;
+    float lw = 0.f;
+    uint32_t bd[kDepth], bi[kDepth];
+    float bw[kDepth];
+    int bn[kDepth];
+    // Buffer j's next chunk: the next 32 postings of the current piece, or of the next descriptor's piece.  Branch-free
+    // apart from the descriptor fetch: with no piece left the chunk is empty (bn <= 0, no lane loads).
+#define THR_ISSUE(j)                                                                                     \
+  {                                                                                                      \
+    if ((j) == 0) flag0 = 0;                                                                             \
+    if (lrem <= 0 && pi < np) {                                                                          \
+      uint32_t x_, y_, z_, w_;                                                                           \
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"                                            \
+                   : "=r"(x_), "=r"(y_), "=r"(z_), "=r"(w_) : "r"(desc_u + (uint32_t)pi * 16u));         \
+      ++pi;                                                                                              \
+      lbase = (const Posting*)(((unsigned long long)y_ << 32) | x_);                                     \
+      loff = (uint32_t)lane;                                                                             \
+      lrem = (int)(z_ & 0xffffu);                                                                        \
+      if ((j) == 0) flag0 = (int)(z_ >> 16);                                                             \
+      lw = __uint_as_float(w_);                                                                          \
+    }                                                                                                    \
+    bn[j] = lrem;                                                                                        \
+    bw[j] = lw;                                                                                          \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t"                                      \
+                 "@p ld.global.nc.v2.u32 {%0, %1}, [%4];\n\t}"                                           \
+                 : "+r"(bd[j]), "+r"(bi[j])                                                              \
+                 : "r"(lane), "r"(lrem), "l"(lbase + loff));                                             \
+    loff += 32u;                                                                                         \
+    lrem -= 32;                                                                                          \
   }
 
-  // ================= consumers =================
-  const uint32_t acc_u = smem_u32(acc);
-  volatile int* v_cnt = &s_int[2];
-  volatile int* v_ovf = &s_int[3];
-  float tau = 0.f;
-  int unit = -1;
-  int want = -1;      // tag filter of the current unit's query (< 0: none)
-  uint32_t s = 0, ph = 0;
-  auto compact = [&](int n) {
-    const uint64_t T = block_compact_topk_t<kSpanThreads, kSpanCap, kSpanBar>(cand, n, a.k, hist, s_prefix, &s_int[0],
-                                                                              &s_int[1], tid);
-    // one ulp below the k-th best score: a later doc that ties with it but has a smaller id must still pass "> tau"
-    tau = f32_from_orderable((uint32_t)(T >> 32) - 1u);
-    if (tid == 0) { s_int[2] = s_int[1]; s_int[3] = 0; }
-    bar_group<kSpanThreads, kSpanBar>();
-  };
-  for (;;) {
-    // Every consumer warp passes here once per chunk, most of them without a posting of their own (a chunk holds
-    // a few hundred postings on average): the common path is kept to the poll, the descriptor, the term barrier
-    // and the release.
-    if (!mbar_try_wait(full_u + s * 8u, ph)) mbar_wait(full_u + s * 8u, ph, a.status, 471);
-    uint32_t dx, dy, dz, dw;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dx), "=r"(dy), "=r"(dz), "=r"(dw) : "r"(desc_u + s * 16u));
-    const uint32_t fl = dx >> 24;
-    const int count = (int)(dx & 0xffffu);
-    if (fl & kFSync) bar_group<kSpanThreads, kSpanBar>();     // the previous term's adds are complete
-    if (tid < count) {
-      const float w = __uint_as_float(dy);
-      const uint32_t acc0 = acc_u - dz * 4u;                  // &acc[doc - doc0] == acc0 + doc * 4
-      const uint32_t pa = ring_u + s * (uint32_t)(kChunk * 8) + (((dx >> 16) & 1u) + (uint32_t)tid) * 8u;
-      uint32_t d[kPerThread];
-      float im[kPerThread], o[kPerThread];
-#pragma unroll
-      for (int u = 0; u < kPerThread; ++u) {
-        d[u] = 0; im[u] = 0.f;
-        if (u == 0 || tid + u * kSpanThreads < count)
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(d[u]), "=f"(im[u]) : "r"(pa + (uint32_t)u * (kSpanThreads * 8u)));
-      }
-#pragma unroll
-      for (int u = 0; u < kPerThread; ++u) {
-        o[u] = 0.f;
-        if (u == 0 || tid + u * kSpanThreads < count) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o[u]) : "r"(acc0 + d[u] * 4u));
-      }
-#pragma unroll
-      for (int u = 0; u < kPerThread; ++u)
-        if (u == 0 || tid + u * kSpanThreads < count)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc0 + d[u] * 4u), "f"(__fadd_rn(o[u], __fmul_rn(w, im[u]))) : "memory");
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_u + s * 8u);
-    if (++s == kStages) { s = 0; ph ^= 1u; }
-    if (!(fl & (kFNewUnit | kFEndSpan | kFEndUnit | kFExit))) continue;
-    if (fl & kFNewUnit) {
-      unit = (int)dw;
-      tau = 0.f;
-      want = (a.tags && a.want) ? a.want[a.units[unit].q] : -1;
-    }
+    // Adds of one chunk: predicated straight-line code (an empty chunk, bn = 0, is a no-op).  ncross / cross_doc:
+    // the lane's threshold crossings.  The slot of doc d is acc[d mod kBlk] (ranges are kBlk-aligned).
+#define THR_ADD(j)                                                                                       \
+  {                                                                                                      \
+    asm volatile(                                                                                        \
+        "{\n\t.reg .pred p, c;\n\t.reg .f32 o, n, x;\n\t.reg .u32 ad;\n\t"                               \
+        "setp.lt.s32 p, %2, %3;\n\t"                                                                     \
+        "and.b32 ad, %4, %9;\n\t"                                                                        \
+        "mad.lo.u32 ad, ad, 4, %5;\n\t"                                                                  \
+        "@p ld.shared.f32 o, [ad];\n\t"                                                                  \
+        "mul.rn.f32 x, %6, %7;\n\t"                                                                      \
+        "add.rn.f32 n, o, x;\n\t"                                                                        \
+        "@p st.shared.f32 [ad], n;\n\t"                                                                  \
+        "setp.gt.and.f32 c, n, %8, p;\n\t"                                                               \
+        "setp.le.and.f32 c, o, %8, c;\n\t"                                                               \
+        "@c add.s32 %0, %0, 1;\n\t"                                                                      \
+        "@c mov.u32 %1, %4;\n\t}"                                                                        \
+        : "+r"(ncross), "+r"(cross_doc)                                                                  \
+        : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(acc_u), "f"(bw[j]), "f"(__uint_as_float(bi[j])), "f"(tau),         \
+          "n"(kBlk - 1)                                                                                  \
+        : "memory");                                                                                     \
+    if (kAnd) {                                                                                          \
+      asm volatile(                                                                                      \
+          "{\n\t.reg .pred p;\n\t.reg .u32 h, ad;\n\t"                                                   \
+          "setp.lt.s32 p, %0, %1;\n\t"                                                                   \
+          "and.b32 ad, %2, %4;\n\t"                                                                      \
+          "add.u32 ad, ad, %3;\n\t"                                                                      \
+          "@p ld.shared.u8 h, [ad];\n\t"                                                                 \
+          "@p add.u32 h, h, 1;\n\t"                                                                      \
+          "@p st.shared.u8 [ad], h;\n\t}"                                                                \
+          :                                                                                              \
+          : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(hit_u), "n"(kBlk - 1)                                 \
+          : "memory");                                                                                   \
+    }                                                                                                    \
+  }
 
-    if (fl & kFEndSpan) {
-      bar_group<kSpanThreads, kSpanBar>();                    // every add of the span has landed
-      for (;;) {
-        const uint32_t sa = acc_u + (uint32_t)tid * 16u;
-        const uint32_t tau_u = tau > 0.f ? __float_as_uint(tau) : 0u;
-        // groups of kScanBatch 16-byte loads in flight, then the tests (the loads of a group do not wait for the
-        // stores of the previous slot)
-#pragma unroll 1
-        for (int j0 = 0; j0 < kScanIters; j0 += kScanBatch) {
-          uint32_t vv[kScanBatch][4];
+    static_assert(kDepth == 4, "the pipeline below is unrolled by hand for four buffers");
 #pragma unroll
-          for (int u = 0; u < kScanBatch; ++u)
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(vv[u][0]), "=r"(vv[u][1]), "=r"(vv[u][2]), "=r"(vv[u][3])
-                         : "r"(sa + (uint32_t)(j0 + u) * (kSpanThreads * 16u)));
-#pragma unroll
-          for (int u = 0; u < kScanBatch; ++u) {
-          const int j = j0 + u;
-          const uint32_t addr = sa + (uint32_t)j * (kSpanThreads * 16u);
-          const uint32_t(&v)[4] = vv[u];
-          // Scores are >= 0, so their bit patterns order like unsigned integers: one integer max of the four slots
-          // decides "all zero" (nothing to do), "none above tau" (zero the slots) or the rare append path, which
-          // repeats the test exactly in fp32 (a negative score, possible only with a caller-made negative idf,
-          // looks large here and is sorted out there).
+    for (int j = 0; j < kDepth; ++j) { bd[j] = 0u; bi[j] = 0u; bn[j] = 0; bw[j] = 0.f; }
+    for (;;) {   // one descriptor list per iteration
+      if (!any_term) break;
+      build();
+      if (np == 0) break;
+      pi = 0;
+      THR_ISSUE(0) THR_ISSUE(1) THR_ISSUE(2) THR_ISSUE(3)
+    for (;;) {   // one range per iteration, its first chunk in buffer 0
+      if (bn[0] <= 0) break;            // the list is used up
+      float tau;
+      asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(tau) : "r"(tau_u));
+      int ncross = 0;
+      uint32_t cross_doc = 0xffffffffu;
+      do {
+        THR_ADD(0) THR_ISSUE(0)
+        THR_ADD(1) THR_ISSUE(1)
+        THR_ADD(2) THR_ISSUE(2)
+        THR_ADD(3) THR_ISSUE(3)
+      } while (bn[0] > 0 && !flag0);   // until buffer 0 starts another range (or is empty: the list is used up)
+      __syncwarp();
+      // ---- the range is complete: collect its candidates, clear its slots ----
+      const bool scan = tau <= 0.f || __any_sync(0xffffffffu, ncross > 1);
+      int appended = 0;
+      if (!scan) {
+        const unsigned cm = __ballot_sync(0xffffffffu, cross_doc != 0xffffffffu);
+        if (cm) {
+          float v = 0.f;
+          uint32_t hc = (uint32_t)need;
+          if (cross_doc != 0xffffffffu) {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(acc_u + (cross_doc & (uint32_t)(kBlk - 1)) * 4u));
+            if (kAnd) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(hc) : "r"(hit_u + (cross_doc & (uint32_t)(kBlk - 1))));
+          }
+          const int before = n_list;
+          append(cross_doc != 0xffffffffu && v > tau && (!kAnd || hc == (uint32_t)need), v, cross_doc);
+          appended = n_list - before;
+        }
+      } else {
+        // Slow path (a unit's warm-up; queries with fewer than k hits): test every slot of the range.  Some lane
+        // crossed (tau <= 0: every first add does), which tells where the range starts.
+        const uint32_t any_doc = __reduce_max_sync(0xffffffffu, cross_doc == 0xffffffffu ? 0u : cross_doc);
+        const bool touched = __any_sync(0xffffffffu, cross_doc != 0xffffffffu);
+        const uint32_t doc0 = any_doc & ~(uint32_t)(kBlk - 1);
+        const int before = n_list;
+        for (int j = 0; touched && j < kBlk / 128; ++j) {
+          if (n_list > kListCap - 128 - 32) compact();
+          const float tcur = __uint_as_float(vsh->tau_bits);
+          uint32_t v[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                       : "r"(acc_u + (uint32_t)(j * 32 + lane) * 16u));
           const uint32_t m = max(max(v[0], v[1]), max(v[2], v[3]));
-          if (m > tau_u) {
-            uint32_t z[4] = {0u, 0u, 0u, 0u};
-            const uint32_t doc = dz + ((uint32_t)j * kSpanThreads + (uint32_t)tid) * 4u;
-            // A doc outside the query's tag is dropped here: it never enters the list, so tau is learnt from
-            // eligible docs only and the result is the exact top-k of the filtered corpus.  One 8-byte load brings
-            // the tags of all four slots (doc is a multiple of 4).
-            int tg[4] = {want, want, want, want};
-            if (want >= 0) {
-              if ((int64_t)doc + 4 <= a.n_docs) {
-                const ushort4 t4 = __ldg((const ushort4*)(a.tags + doc));
-                tg[0] = t4.x; tg[1] = t4.y; tg[2] = t4.z; tg[3] = t4.w;
-              } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tg[c] = (int64_t)doc + c < a.n_docs ? (int)a.tags[doc + c] : -1;
-              }
-            }
+          uint32_t hc4 = 0u;
+          if (kAnd) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hc4) : "r"(hit_u + (uint32_t)(j * 32 + lane) * 4u));
+          if (__any_sync(0xffffffffu, m != 0u)) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float x = __uint_as_float(v[c]);
-              if (x > tau && tg[c] == want) {
-                const int pos = atomicAdd(&s_int[2], 1);
-                if (pos < kSpanCap) cand[pos] = pack_key(x, doc + c);
-                else { *v_ovf = 1; z[c] = v[c]; }              // stays in the accumulator for the next scan
-              }
+              const uint32_t doc = doc0 + (uint32_t)(j * 32 + lane) * 4u + c;
+              const bool all = !kAnd || ((hc4 >> (8 * c)) & 255u) == (uint32_t)need;
+              append(x > tcur && x > 0.f && all, x, doc);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3])
-                         : "memory");
-          } else if (m != 0u) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
-          }
           }
         }
-        bar_group<kSpanThreads, kSpanBar>();
-        const int n = min(*v_cnt, kSpanCap);
-        const bool ovf = *v_ovf != 0;
-        // Under a tag filter every doc above tau costs a tag load whether it is eligible or not, so tau has to
-        // follow the eligible docs closely: compact as soon as the list holds a few more than k entries.
-        const int limit = want >= 0 ? min(kSpanCap / 2, max(2 * a.k, 256)) : kSpanCap / 2;
-        if (!ovf && n <= limit) break;                        // uniform: the counters are stable here
-        bar_group<kSpanThreads, kSpanBar>();                  // everyone has read them
-        if (n > a.k) compact(n);
-        else if (tid == 0) s_int[3] = 0;                      // (cannot overflow with n <= k; keep the flag sane)
-        if (!ovf) break;
+        appended = n_list - before;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kBlk / 128; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(acc_u + (uint32_t)(j * 32 + lane) * 16u), "r"(0u)
+                     : "memory");
+      if (kAnd) {
+#pragma unroll
+        for (int j = 0; j < kBlk / 128; ++j)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(hit_u + (uint32_t)(j * 32 + lane) * 4u), "r"(0u) : "memory");
+      }
+      __syncwarp();
+      if (appended) {
+        if (n_list > kListHigh) compact();
+        else raise_tau();
       }
     }
-    if (fl & kFEndUnit) {
-      bar_group<kSpanThreads, kSpanBar>();
-      int n = min(*v_cnt, kSpanCap);
-      bar_group<kSpanThreads, kSpanBar>();
-      if (n > a.k) {
-        (void)block_compact_topk_t<kSpanThreads, kSpanCap, kSpanBar>(cand, n, a.k, hist, s_prefix, &s_int[0], &s_int[1], tid);
-        n = s_int[1];
-        bar_group<kSpanThreads, kSpanBar>();
-      }
-      // bitonic sort (descending) of <= 256 keys padded with 0
-      for (int i = n + tid; i < kMaxSelB; i += kSpanThreads) cand[i] = 0ull;
-      bar_group<kSpanThreads, kSpanBar>();
-      for (int size = 2; size <= kMaxSelB; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-          if (tid < kMaxSelB / 2) {
-            const int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
-            const int hi = lo + stride;
-            const bool desc_block = ((lo & size) == 0);
-            const uint64_t x = cand[lo], y = cand[hi];
-            const bool swap = desc_block ? (y > x) : (x > y);
-            if (swap) { cand[lo] = y; cand[hi] = x; }
+    }
+#undef THR_ISSUE
+#undef THR_ADD
+
+    // ================= unit end: the CTA's k best =================
+    __syncthreads();
+    {
+      const uint32_t tb = vsh->tau_bits;
+      n_list = list_filter(list, n_list, tb, lane);
+      if (lane == 0 && n_list) atomicAdd(&sh->n_total, n_list);
+    }
+    __syncthreads();
+    const int n_total = vsh->n_total;
+    int n_fin;
+    if (n_total <= kMaxSelB) {
+      int pos = 0;
+      if (lane == 0 && n_list) pos = atomicAdd(&sh->n_out, n_list);
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      for (int i = lane; i < n_list; i += 32) scratch[pos + i] = __ldcg(list + i);
+      n_fin = n_total;
+    } else {
+      // radix select of the k-th largest key over the warps' lists (keys are distinct: they carry the doc id)
+      if (tid == 0) { sh->prefix = 0ull; sh->want_sel = a.k; }
+      for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = tid; i < 256; i += blockDim.x) sh->hist2[i] = 0u;
+        __syncthreads();
+        const uint64_t prefix = sh->prefix;
+        for (int i = lane; i < n_list; i += 32) {
+          const uint64_t key = __ldcg(list + i);
+          if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+            atomicAdd(&sh->hist2[(uint32_t)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+          const int wsel = sh->want_sel;
+          int d, above;
+          if (radix_find_digit(sh->hist2, wsel, tid, &d, &above)) {
+            sh->want_sel = wsel - above;
+            sh->prefix = prefix | ((unsigned long long)d << shift);
           }
-          bar_group<kSpanThreads, kSpanBar>();
+        }
+        __syncthreads();
+      }
+      const uint64_t T = sh->prefix;
+      for (int i = lane; i < n_list; i += 32) {
+        const uint64_t key = __ldcg(list + i);
+        if (key >= T) {
+          const int pos = atomicAdd(&sh->n_out, 1);
+          if (pos < kMaxSelB) scratch[pos] = key;
         }
       }
-      if (tid == 0) a.part_cnt[unit] = n;
-      for (int i = tid; i < n; i += kSpanThreads) a.part_keys[(size_t)unit * a.k + i] = cand[i];
-      bar_group<kSpanThreads, kSpanBar>();
-      if (tid == 0) { s_int[2] = 0; s_int[3] = 0; }
-      bar_group<kSpanThreads, kSpanBar>();
+      n_fin = min(n_total, a.k);
     }
-    if (fl & kFExit) break;
+    __syncthreads();
+    n_fin = min(n_fin, min(vsh->n_out, kMaxSelB));
+    for (int i = n_fin + tid; i < kMaxSelB; i += blockDim.x) scratch[i] = 0ull;
+    __syncthreads();
+    for (int size = 2; size <= kMaxSelB; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (tid < kMaxSelB / 2) {
+          const int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
+          const int hi = lo + stride;
+          const bool desc_block = ((lo & size) == 0);
+          const uint64_t x = scratch[lo], y = scratch[hi];
+          const bool swap = desc_block ? (y > x) : (x > y);
+          if (swap) { scratch[lo] = y; scratch[hi] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    const int n_keep = min(n_fin, a.k);
+    if (tid == 0) a.part_cnt[unit] = n_keep;
+    for (int i = tid; i < n_keep; i += blockDim.x) a.part_keys[(size_t)unit * a.k + i] = scratch[i];
+    for (int i = tid; i < kHistBins; i += blockDim.x) sh->hist[i] = 0u;
+    if (tid == 0) { sh->n_total = 0; sh->n_out = 0; }
   }
 }
 
-__global__ void bm25_df_kernel(const int64_t* skip, int n_blk, int V, int64_t* df) {
+// df per term; also checks idf >= 0: the kernel relies on a doc's partial sums never decreasing.
+__global__ void bm25_df_kernel(const int64_t* skip, const float* idf, int n_blk, int V, int64_t* df,
+                               thr_dev_status* status) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V) return;
   df[t] = skip[(size_t)(t + 1) * n_blk] - skip[(size_t)t * n_blk];
+  if (!(idf[t] >= 0.f)) dev_report(status, THR_EINVAL, 461, t);
 }
 
 // cost[q] = total postings of the query's terms + term_cost per (term with postings, range): the kernel's time
-// follows the number of (term, span) visits at least as much as the number of postings.
+// follows the number of (term, range) visits at least as much as the number of postings.  Also resets the
+// query's shared threshold.
 __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, const int64_t* df, int V,
                                  int B, int n_blk, long long term_cost, unsigned long long* keys,
-                                 thr_dev_status* status) {
+                                 unsigned* tau_q, thr_dev_status* status) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
-  // more terms than the kernel has lanes for: reported by thr_sync, never silently truncated
+  tau_q[q] = 0u;
+  // more terms than a warp has lanes for: reported by thr_sync, never silently truncated
   if (q_off[q + 1] - q_off[q] > kMaxTerms) dev_report(status, THR_EINVAL, 460, q);
   long long c = 0;
   for (int i = q_off[q]; i < q_off[q + 1]; ++i) {
@@ -510,10 +621,11 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 }
 
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
-// per-range overhead (kRangeCost postings' worth of pipeline work), so light queries are split as well.
-constexpr unsigned long long kSpanRangeCost = 400;   // the scan of a range is worth about this many postings
-constexpr long long kSpanTermCost = 75;         // per (term, range) on top of the term's postings
-constexpr int kSpanUnitsPerCta = 2;
+// per-range overhead (range_cost postings' worth of work: skip loads, clearing the slots), so light queries are
+// split as well.
+constexpr unsigned long long kRangeCostDefault = 64;   // clearing + bookkeeping of a range, in postings
+constexpr long long kTermCostDefault = 24;             // per (term, range) on top of the term's postings
+constexpr int kUnitsPerCtaDefault = 2;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_slots, unsigned long long kRangeCost,
                                                           Unit* units, int* unit_base,
@@ -529,7 +641,7 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long lon
   atomicAdd(&s_tot, part);
   __syncthreads();
   unsigned long long target = s_tot / (unsigned long long)num_slots + 1;
-  if (target < 65536ull) target = 65536ull;
+  if (target < 16384ull) target = 16384ull;
   for (int q0 = 0; q0 < B; q0 += 1024) {
     const int q = q0 + tid;
     int nu = 0;
@@ -601,17 +713,19 @@ __global__ void __launch_bounds__(256) bm25_merge_kernel(const uint64_t* part_ke
     keys[i] = key;
   }
   __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (P >> 1); i += 256) {
-        int lo = ((i / stride) * (stride << 1)) + (i % stride);
-        int hi = lo + stride;
-        bool desc_block = ((lo & size) == 0);
-        uint64_t x = keys[lo], y = keys[hi];
-        bool swap = desc_block ? (y > x) : (x > y);
-        if (swap) { keys[lo] = y; keys[hi] = x; }
+  if (u1 - u0 > 1) {   // a single unit's list is already sorted
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < (P >> 1); i += 256) {
+          int lo = ((i / stride) * (stride << 1)) + (i % stride);
+          int hi = lo + stride;
+          bool desc_block = ((lo & size) == 0);
+          uint64_t x = keys[lo], y = keys[hi];
+          bool swap = desc_block ? (y > x) : (x > y);
+          if (swap) { keys[lo] = y; keys[hi] = x; }
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   int n = 0;
@@ -641,6 +755,11 @@ struct thr_bm25_state {
   int64_t id_base;
   int64_t* df;  // [V] device
   const uint16_t* tags;  // [n_docs] device, nullable
+  // planner tuning (per handle; THR_BM25_* environment variables are read once, when the index is set)
+  int units_per_cta;
+  long long range_cost, term_cost;
+  int warps;    // warps per CTA of bm25_range_kernel (0: as many as shared memory holds)
+  int pf_dist;  // L2 prefetch distance in ranges (< 0: half a round of the CTA's warps)
 };
 
 void thr_bm25_state_free(thr_handle* h) {
@@ -650,6 +769,10 @@ void thr_bm25_state_free(thr_handle* h) {
     h->bm25 = nullptr;
   }
 }
+
+static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                          const int32_t* want, int require_all, int64_t* out_ids, float* out_scores,
+                          int32_t* out_count, void* stream);
 
 extern "C" {
 
@@ -674,14 +797,31 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
   if (!st) return thr_fail(h, THR_ENOMEM, "out of host memory");
   st->skip = skip; st->post = postings; st->idf = idf; st->n_docs = n_docs; st->n_blk = n_blk;
   st->blk_docs = blk_docs; st->blk_shift = shift; st->V = V; st->id_base = id_base;
+  const char* e1 = getenv("THR_BM25_TERM_COST");
+  st->term_cost = e1 ? atoll(e1) : kTermCostDefault;
+  e1 = getenv("THR_BM25_UNITS_PER_SM");
+  st->units_per_cta = e1 ? atoi(e1) : kUnitsPerCtaDefault;
+  if (st->units_per_cta < 1) st->units_per_cta = 1;
+  e1 = getenv("THR_BM25_RANGE_COST");
+  st->range_cost = e1 ? atoll(e1) : (long long)kRangeCostDefault;
+  e1 = getenv("THR_BM25_WARPS");
+  st->warps = e1 ? atoi(e1) : 0;
+  e1 = getenv("THR_BM25_PREFETCH");
+  st->pf_dist = e1 ? atoi(e1) : -1;
   cudaError_t e = cudaMalloc((void**)&st->df, (size_t)V * sizeof(int64_t));
   if (e != cudaSuccess) { free(st); return thr_fail(h, THR_ENOMEM, "cudaMalloc(df): %s", cudaGetErrorString(e)); }
-  bm25_df_kernel<<<(V + 255) / 256, 256>>>(skip, n_blk, V, st->df);
+  bm25_df_kernel<<<(V + 255) / 256, 256>>>(skip, idf, n_blk, V, st->df, h->d_status);
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(st->df); free(st);
     return thr_fail(h, THR_ECUDA, "bm25_df_kernel: %s", cudaGetErrorString(e));
+  }
+  if (h->h_status->code == THR_EINVAL && h->h_status->where == 461) {
+    const long long t = h->h_status->aux;
+    h->h_status->code = 0;
+    cudaFree(st->df); free(st);
+    return thr_fail(h, THR_EINVAL, "thr_bm25_index_set: idf[%lld] is negative or NaN (idf must be >= 0)", t);
   }
   h->launches++;
   h->bm25 = st;
@@ -698,12 +838,42 @@ int thr_bm25_tags_set(thr_handle* h, const uint16_t* tags) {
 
 int thr_bm25_topk(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
                   int64_t* out_ids, float* out_scores, int32_t* out_count, void* stream) {
-  return thr_bm25_topk_tagged(h, q_terms, q_off, B, k, nullptr, out_ids, out_scores, out_count, stream);
+  return bm25_topk_impl(h, q_terms, q_off, B, k, nullptr, 0, out_ids, out_scores, out_count, stream);
 }
 
 int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
                          const int32_t* want, int64_t* out_ids, float* out_scores, int32_t* out_count,
                          void* stream) {
+  return bm25_topk_impl(h, q_terms, q_off, B, k, want, 0, out_ids, out_scores, out_count, stream);
+}
+
+int thr_bm25_topk_ex(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                     const int32_t* want, int flags, int64_t* out_ids, float* out_scores,
+                     int32_t* out_count, void* stream) {
+  if (h && (flags & ~THR_BM25_REQUIRE_ALL)) return thr_fail(h, THR_EINVAL, "thr_bm25_topk_ex: unknown flag bits 0x%x", flags);
+  return bm25_topk_impl(h, q_terms, q_off, B, k, want, (flags & THR_BM25_REQUIRE_ALL) ? 1 : 0, out_ids, out_scores,
+                        out_count, stream);
+}
+
+}  // extern "C"
+
+template <int kBlk, bool kAnd>
+static cudaError_t launch_range2(const Bm25Args& a, int grid, int warps, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(bm25_range_kernel<kBlk, kAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(bm25_range_kernel<kBlk, kAnd>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) return e;
+  bm25_range_kernel<kBlk, kAnd><<<grid, warps * 32, smem, s>>>(a);
+  return cudaSuccess;
+}
+template <int kBlk>
+static cudaError_t launch_range(const Bm25Args& a, int grid, int warps, size_t smem, cudaStream_t s) {
+  return a.require_all ? launch_range2<kBlk, true>(a, grid, warps, smem, s) : launch_range2<kBlk, false>(a, grid, warps, smem, s);
+}
+
+static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* q_off, int B, int k,
+                          const int32_t* want, int require_all, int64_t* out_ids, float* out_scores,
+                          int32_t* out_count, void* stream) {
   if (!h) return THR_EINVAL;
   cudaSetDevice(h->device);
   thr_bm25_state* st = h->bm25;
@@ -713,7 +883,15 @@ int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q
   if (B == 0) return THR_OK;
   THR_REQUIRE(h, q_terms && q_off && out_ids && out_scores && out_count, "thr_bm25_topk: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
-  // scratch: cost keys | units | order | unit_base | counters | partial lists
+  const int grid = h->num_sms;
+  // warps per CTA: one accumulator (blk_docs fp32 slots) each, as many as shared memory holds (at most 32)
+  const size_t fixed = (size_t)kListCap * 8 + sizeof(RangeShared) + 256;
+  const size_t per_warp = (size_t)st->blk_docs * (require_all ? 5 : 4) + kDescCap * 16;   // fp32 slots (+ u8 hit counts) + piece list
+  int warps = (int)((232448 - fixed) / per_warp);
+  if (warps > 32) warps = 32;
+  if (st->warps > 0 && st->warps < warps) warps = st->warps;
+  const size_t smem = (size_t)warps * per_warp + fixed;
+  // scratch: cost keys | units | order | unit_base | counters | partial lists | tau per query | per-warp lists
   const size_t max_units = (size_t)B * kMaxUnitsPerQuery;
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_keys = 0;
@@ -723,7 +901,9 @@ int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q
   const size_t o_cnt = o_base + up((size_t)(B + 1) * 4);
   const size_t o_pcnt = o_cnt + 256;
   const size_t o_pkeys = o_pcnt + up(max_units * 4);
-  const size_t need = o_pkeys + up(max_units * (size_t)k * 8);
+  const size_t o_tau = o_pkeys + up(max_units * (size_t)k * 8);
+  const size_t o_wl = o_tau + up((size_t)B * 4);
+  const size_t need = o_wl + up((size_t)grid * warps * kListCap * 8);
   uint8_t* ws = (uint8_t*)thr_scratch(h, need);
   if (!ws) return THR_ENOMEM;
   unsigned long long* keys = (unsigned long long*)(ws + o_keys);
@@ -736,25 +916,12 @@ int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q
   uint64_t* part_keys = (uint64_t*)(ws + o_pkeys);
 
   int tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
-
   // Work is cut into about `grid * units_per_cta` units of equal cost (heaviest first, fetched dynamically).
-  static int units_per_cta = 0;
-  static long long range_cost = -1, term_cost = 0;
-  if (!units_per_cta) {
-    const char* t = getenv("THR_BM25_TERM_COST");
-    term_cost = t ? atoll(t) : (long long)kSpanTermCost;
-    const char* e = getenv("THR_BM25_UNITS_PER_SM");   // measured flat between 1 and 4 at 10M docs
-    units_per_cta = e ? atoi(e) : kSpanUnitsPerCta;
-    if (units_per_cta < 1) units_per_cta = 1;
-    e = getenv("THR_BM25_RANGE_COST");
-    range_cost = e ? atoll(e) : (long long)kSpanRangeCost;
-  }
-  const int grid = kSpanCtas * h->num_sms;
-  bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, st->n_blk, term_cost, keys,
-                                                   h->d_status);
+  bm25_cost_kernel<<<(B + 255) / 256, 256, 0, s>>>(q_terms, q_off, st->df, st->V, B, st->n_blk, st->term_cost, keys,
+                                                   (unsigned*)(ws + o_tau), h->d_status);
   THR_CHECK_LAUNCH(h, "bm25_cost_kernel");
-  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, grid * units_per_cta, (unsigned long long)range_cost, units,
-                                      unit_base, total_units, counter);
+  bm25_plan_kernel<<<1, 1024, 0, s>>>(keys, B, st->n_blk, grid * st->units_per_cta, (unsigned long long)st->range_cost,
+                                      units, unit_base, total_units, counter);
   THR_CHECK_LAUNCH(h, "bm25_plan_kernel");
   bm25_order_kernel<<<32, 256, 0, s>>>(units, total_units, order);
   thr_prof_end(h, tok, s);
@@ -766,13 +933,20 @@ int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q
   a.q_terms = q_terms; a.q_off = q_off; a.order = order; a.units = units; a.total_units = total_units;
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.tags = want ? st->tags : nullptr; a.want = want;
+  a.wlists = (uint64_t*)(ws + o_wl); a.tau_q = (unsigned*)(ws + o_tau); a.require_all = require_all;
+  a.pf_dist = st->pf_dist >= 0 ? st->pf_dist : warps * kGrab / 2;
   a.status = h->d_status;
-  THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpanSmem));
-  THR_CUDA(h, cudaFuncSetAttribute(bm25_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   tok = thr_prof_begin(h, THR_PROF_BM25, s);
-  bm25_span_kernel<<<grid, kSpanThreads + 32, kSpanSmem, s>>>(a);
+  cudaError_t le;
+  switch (st->blk_docs) {
+    case 2048: le = launch_range<2048>(a, grid, warps, smem, s); break;
+    case 1024: le = launch_range<1024>(a, grid, warps, smem, s); break;
+    case 512: le = launch_range<512>(a, grid, warps, smem, s); break;
+    default: le = launch_range<256>(a, grid, warps, smem, s); break;
+  }
   thr_prof_end(h, tok, s);
-  THR_CHECK_LAUNCH(h, "bm25_span_kernel");
+  if (le != cudaSuccess) return thr_fail(h, THR_ECUDA, "bm25_range_kernel attributes: %s", cudaGetErrorString(le));
+  THR_CHECK_LAUNCH(h, "bm25_range_kernel");
   tok = thr_prof_begin(h, THR_PROF_BM25_PREP, s);
   size_t merge_slots = 32;
   while (merge_slots < (size_t)kMaxUnitsPerQuery * k) merge_slots <<= 1;
@@ -783,5 +957,3 @@ int thr_bm25_topk_tagged(thr_handle* h, const int32_t* q_terms, const int32_t* q
   THR_CHECK_LAUNCH(h, "bm25_merge_kernel");
   return THR_OK;
 }
-
-}  // extern "C"

@@ -143,9 +143,11 @@ class Engine:
         self._keep["bm25_tags"] = tags
         self._check(self._lib.thr_bm25_tags_set(self._h, _ptr(tags)))
 
-    def bm25_topk(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int, want: Optional[torch.Tensor] = None
-                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> ids [B,k] int64, scores [B,k] float32, count [B] int32.  want: as in dense_topk."""
+    def bm25_topk(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int, want: Optional[torch.Tensor] = None,
+                  require_all: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> ids [B,k] int64, scores [B,k] float32, count [B] int32.  want: as in dense_topk.
+        require_all: AND semantics of `tsv @@ plainto_tsquery` (20260114_rag2_schema.sql:369) — only docs that contain
+        every distinct term of the query."""
         q_terms = self._dev(q_terms, torch.int32, "q_terms")
         q_off = self._dev(q_off, torch.int32, "q_off")
         B = q_off.numel() - 1
@@ -156,8 +158,9 @@ class Engine:
         ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((B, k), dtype=torch.float32, device=self.device)
         cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
-        self._check(self._lib.thr_bm25_topk_tagged(self._h, _ptr(q_terms), _ptr(q_off), B, k, _ptr(want), _ptr(ids),
-                                                   _ptr(sc), _ptr(cnt), self._stream()))
+        flags = _lib.BM25_REQUIRE_ALL if require_all else 0
+        self._check(self._lib.thr_bm25_topk_ex(self._h, _ptr(q_terms), _ptr(q_off), B, k, _ptr(want), flags, _ptr(ids),
+                                               _ptr(sc), _ptr(cnt), self._stream()))
         return ids, sc, cnt
 
     # -- K3 fusion --------------------------------------------------------------------------

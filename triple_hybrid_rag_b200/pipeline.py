@@ -130,13 +130,16 @@ class TripleHybridSearcher:
     def search(self, Q: torch.Tensor, q_terms: torch.Tensor, q_off: torch.Tensor,
                graph_ids: Optional[torch.Tensor], weights: Optional[torch.Tensor] = None,
                k_sem: int = 100, k_lex: int = 100, top_k: int = 100, margin: int = 28,
-               tie_mode: int = _lib.TIE_CHUNK_ID, rrf_k: int = 60, want: Optional[torch.Tensor] = None) -> SearchOutput:
+               tie_mode: int = _lib.TIE_CHUNK_ID, rrf_k: int = 60, want: Optional[torch.Tensor] = None,
+               require_all: bool = False) -> SearchOutput:
         """want: int32 [B] on the device — per query, the tag its semantic and lexical hits must carry (< 0: any);
-        needs set_tags.  The graph list is an input and is taken as given."""
+        needs set_tags.  require_all: AND semantics of the lexical channel (thr_bm25_topk_ex).  The graph list is an
+        input and is taken as given.  SearchOutput.gap is K1's exactness certificate of THIS shard (compare with
+        dense_error_bound; `certify` does it on the host)."""
         eng, dev = self.engine, self.engine.device
         B = Q.shape[0]
         d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin, want=want)
-        l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex, want=want)
+        l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex, want=want, require_all=require_all)
         if self.world > 1:
             d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt = self._exchange(B, k_sem, k_lex, d_ids, d_sc, d_cnt,
                                                                     l_ids, l_sc, l_cnt)
