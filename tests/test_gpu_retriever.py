@@ -174,7 +174,7 @@ def test_resident_index_end_to_end_vs_oracle(engine, settings):
     qv = (emb[123] + 0.3 * torch.randn(D, generator=g))
     qtok = torch.randn((24, d), generator=g)
     r = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"find me": qv.tolist()}), query_planner=MagicMock(),
-                         index=ix, token_encoder=lambda q: qtok, graph_enabled=False)
+                         index=ix, token_encoder=lambda q: qtok, graph_enabled=False, lexical_match="any")
 
     # semantic channel == oracle dense top-k on the bf16-rounded, normalised inputs
     rows = asyncio.run(r._semantic_search("find me", None, 50))
@@ -207,9 +207,36 @@ def test_resident_index_end_to_end_vs_oracle(engine, settings):
     assert asyncio.run(r._lexical_search(kw, "no-such-collection", 10)) == []
     sem_b = asyncio.run(r._semantic_search("find me", "b", 10))
     assert len(sem_b) == 10 and all(chunks[ix.id_of[x["child_id"]]]["collection"] == "b" for x in sem_b)
-    sem_all = asyncio.run(r._semantic_search("find me", None, 300))
+    sem_all = asyncio.run(r._semantic_search("find me", None, 250))
+    with pytest.raises(ValueError, match="252"):      # the reference RPC honours any p_limit; K1 says so instead of clamping
+        asyncio.run(r._semantic_search("find me", None, 300))
+    with pytest.raises(ValueError, match="256"):
+        asyncio.run(r._lexical_search(kw, None, 300))
     assert [x["child_id"] for x in sem_b] == [x["child_id"] for x in sem_all
                                               if chunks[ix.id_of[x["child_id"]]]["collection"] == "b"][:10]
+
+    # the reference's own predicate: every keyword must match (`tsv @@ plainto_tsquery`, 20260114_rag2_schema.sql:369);
+    # a repeated keyword counts once; an unknown keyword empties the result
+    r_all = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"find me": qv.tolist()}), index=ix)
+    assert r_all.lexical_match == "all"
+    rows_all = asyncio.run(r_all._lexical_search(["w3", "w17", "W3"], None, 50))
+    ai, as_, ac = ob.bm25_topk(orc, [[ix.vocab["w3"], ix.vocab["w17"]]], 50, require_all=True)
+    assert ac[0] > 0 and [x["child_id"] for x in rows_all] == [f"c{i}" for i in ai[0, :ac[0]]]
+    assert np.array_equal(np.array([x["rank"] for x in rows_all], dtype=np.float32), as_[0, :ac[0]])
+    assert all({"w3", "w17"} <= set(R.tokenize(chunks[ix.id_of[x["child_id"]]]["text"])) for x in rows_all)
+    assert asyncio.run(r_all._lexical_search(kw, None, 50)) == []
+
+    # the reference-shaped reranker: document TEXTS in, one score in [0, 1] per text out (reranker.py:287-291)
+    rr = R.GpuMaxSimReranker(ix, lambda q: qtok)
+    texts = [chunks[5]["text"], "a text the index has never seen", parents["p3"]["text"]]
+    sc = asyncio.run(rr._rerank_batch_native("find me", texts))
+    qt_ = (qtok / qtok.norm(dim=-1, keepdim=True)).to(torch.bfloat16).float().numpy()[None]
+    kids = [i for i, c in enumerate(chunks) if c["parent_id"] == "p3"]
+    w5 = om.maxsim(qt_, tok.float().numpy(), np.array([[ix._rows_first(chunks[5]["text"])] + kids]))[0]
+    to01 = lambda v: float(np.clip(0.5 * (v / 24 + 1.0), 0, 1))
+    assert np.isclose(sc[0], to01(w5[0]), rtol=1e-3) and sc[1] == 0.5
+    assert np.isclose(sc[2], max(to01(v) for v in w5[1:]), rtol=1e-3)
+    assert R.Reranker is R.GpuMaxSimReranker
 
     # whole pipeline, MaxSim rerank included, against the oracle
     settings.rag2_rerank_top_k, settings.rag2_safety_threshold, settings.rag2_denoise_alpha = 20, 0.0, 0.0
@@ -234,7 +261,7 @@ def test_retrieve_batch_matches_oracle_fusion(engine):
     n, D = 900, 64
     chunks, emb, parents = _corpus(n, D, seed=6)
     ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=1024)
-    r = GpuRAG2Retriever(org_id="t", index=ix)
+    r = GpuRAG2Retriever(org_id="t", index=ix, lexical_match="any")
     g = torch.Generator().manual_seed(3)
     Q = torch.randn((5, D), generator=g)
     kws = [["w1", "w9"], ["w2"], ["zzz"], ["w5", "w6", "w7"], []]
@@ -264,7 +291,7 @@ def test_coalescing_front_end_equals_direct_batches(engine):
     n, D = 900, 64
     chunks, emb, parents = _corpus(n, D, seed=6)
     ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=1024)
-    r = GpuRAG2Retriever(org_id="t", index=ix)
+    r = GpuRAG2Retriever(org_id="t", index=ix, lexical_match="any")
     g = torch.Generator().manual_seed(4)
     nq = 12
     Q = torch.randn((nq, D), generator=g)
@@ -289,15 +316,44 @@ def test_coalescing_front_end_equals_direct_batches(engine):
             assert out[b] and all(chunks[ix.id_of[c.child_id]]["collection"] == colls[b] for c in out[b])
 
 
+def test_front_end_serialises_overlapping_batches(engine):
+    """overlapping batches must not share the handle's scratch.  Many small batches are in flight at once
+    (max_batch 4, no waiting); every request must come back exactly as a direct call returns it."""
+    from triple_hybrid_rag_b200.frontend import CoalescingFrontEnd
+    n, D = 3000, 64
+    chunks, emb, parents = _corpus(n, D, seed=12)
+    ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=256)
+    r = GpuRAG2Retriever(org_id="t", index=ix, lexical_match="any")
+    g = torch.Generator().manual_seed(5)
+    nq = 64
+    Q = torch.randn((nq, D), generator=g)
+    kws = [[f"w{(7 * b) % 60}", f"w{(11 * b + 3) % 200}", f"w{b % 17}"] for b in range(nq)]
+    direct = [r.retrieve_batch(["q"], Q[b:b + 1], [kws[b]], top_k=20, k_sem=20, k_lex=20)[0] for b in range(nq)]
+
+    def batch_fn(queries, vectors, keywords, graph, collections):
+        return r.retrieve_batch(queries, vectors, keywords, graph_ids=graph, top_k=20, k_sem=20, k_lex=20)
+
+    async def go():
+        fe = CoalescingFrontEnd(batch_fn, max_batch=4, max_wait_ms=0.0)
+        out = await asyncio.gather(*[fe.retrieve_candidates("q", Q[b], kws[b]) for b in range(nq)])
+        await fe.drain()
+        fe.close()
+        return fe, out
+    fe, out = asyncio.run(go())
+    assert len(fe.batches) >= nq // 4
+    key = lambda lst: [(c.child_id, c.rrf_score.hex(), c.lexical_rank, c.semantic_rank) for c in lst]
+    assert [key(x) for x in out] == [key(x) for x in direct]
+
+
 def test_resident_index_save_load(engine, tmp_path):
     chunks, emb, parents = _corpus(300, 64, seed=8)
     ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=256)
-    r = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"q": emb[5].tolist()}), index=ix)
+    r = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"q": emb[5].tolist()}), index=ix, lexical_match="any")
     want_l = asyncio.run(r._lexical_search(["w2", "w11"], None, 20))
     want_s = asyncio.run(r._semantic_search("q", None, 20))
     ix.save(tmp_path / "ix.pt")
     ix2 = ResidentIndex.load(engine, tmp_path / "ix.pt")
-    r2 = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"q": emb[5].tolist()}), index=ix2)
+    r2 = GpuRAG2Retriever(org_id="t", embedder=_Embedder({"q": emb[5].tolist()}), index=ix2, lexical_match="any")
     assert asyncio.run(r2._lexical_search(["w2", "w11"], None, 20)) == want_l
     assert asyncio.run(r2._semantic_search("q", None, 20)) == want_s
 

@@ -77,3 +77,22 @@ def test_save_load_roundtrip(tmp_path):
     assert torch.equal(idx.idf.view(torch.int32), back.idf.view(torch.int32))
     assert (idx.n_docs, idx.blk_docs, idx.V, idx.nnz, idx.k1, idx.b, idx.avgdl) == \
            (back.n_docs, back.blk_docs, back.V, back.nnz, back.k1, back.b, back.avgdl)
+
+
+def test_tokenizer_hook_portuguese():
+    """The linguistic hook in front of the lexical channel: stop words dropped, plurals folded,
+    and the same callable serves corpus and queries."""
+    from triple_hybrid_rag_b200.retriever import Tokenizer, tokenize
+    tk = Tokenizer.portuguese()
+    assert tk("Os contratos de pagamento e as condições") == ["contrato", "pagamento", "condição"]
+    assert tk("contrato") == tk("CONTRATOS") and tk("de para com") == []
+    assert Tokenizer()("Os contratos") == tokenize("Os contratos") == ["os", "contratos"]
+
+
+def test_pad_dim_keeps_dot_products():
+    import torch
+    from triple_hybrid_rag_b200.retriever import pad_dim
+    x = torch.randn(5, 4000).to(torch.bfloat16)      # the RAG 1.0 halfvec(4000) width
+    p = pad_dim(x)
+    assert p.shape == (5, 4032) and torch.equal(p[:, :4000], x) and not p[:, 4000:].any()
+    assert torch.equal(pad_dim(p), p)

@@ -625,7 +625,7 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 // split as well.
 constexpr unsigned long long kRangeCostDefault = 64;   // clearing + bookkeeping of a range, in postings
 constexpr long long kTermCostDefault = 24;             // per (term, range) on top of the term's postings
-constexpr int kUnitsPerCtaDefault = 2;
+constexpr int kUnitsPerCtaDefault = 1;   // measured at 10M / 1.25M docs, batch 256: 1 -> 1.13 / 0.22 ms, 2 -> 1.21 / 0.26, 4 -> 1.23 / 0.33
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_slots, unsigned long long kRangeCost,
                                                           Unit* units, int* unit_base,
@@ -759,7 +759,7 @@ struct thr_bm25_state {
   int units_per_cta;
   long long range_cost, term_cost;
   int warps;    // warps per CTA of bm25_range_kernel (0: as many as shared memory holds)
-  int pf_dist;  // L2 prefetch distance in ranges (< 0: half a round of the CTA's warps)
+  int pf_dist;  // L2 prefetch distance in ranges (THR_BM25_PREFETCH; < 0: the default, none)
 };
 
 void thr_bm25_state_free(thr_handle* h) {
@@ -934,7 +934,10 @@ static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* 
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.tags = want ? st->tags : nullptr; a.want = want;
   a.wlists = (uint64_t*)(ws + o_wl); a.tau_q = (unsigned*)(ws + o_tau); a.require_all = require_all;
-  a.pf_dist = st->pf_dist >= 0 ? st->pf_dist : warps * kGrab / 2;
+  // L2 prefetch of a later grab: off by default.  Measured at 10M docs (ncu dram__bytes_read): distance 0 -> 1.217 ms,
+  // 2.42 GB read; 8 -> 1.173 ms; 16 -> 1.183 ms, 2.96 GB; 50 -> 1.206 ms, 3.35 GB (2.66 GB algorithmic): the 4 %
+  // it buys are paid with 20-40 % more DRAM traffic, which the dense kernel sharing the step cannot spare.
+  a.pf_dist = st->pf_dist >= 0 ? st->pf_dist : 0;
   a.status = h->d_status;
   tok = thr_prof_begin(h, THR_PROF_BM25, s);
   cudaError_t le;

@@ -34,6 +34,10 @@ class Engine:
             raise _lib.ThrError(rc, lib.thr_last_error(None).decode())
         self._h = h
         self._keep = {}  # tensors the C side references (indices are not copied)
+        # One thread at a time per handle (include/thr.h): a batch is a SEQUENCE of calls sharing the handle's scratch,
+        # so callers that may overlap (CoalescingFrontEnd's executor threads) hold this lock around a whole batch.
+        import threading
+        self.lock = threading.RLock()
 
     # -- plumbing ---------------------------------------------------------------------------
     def close(self):

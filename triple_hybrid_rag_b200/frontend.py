@@ -29,12 +29,16 @@ class _Pending:
 
 class CoalescingFrontEnd:
     """`batch_fn(queries, query_vectors [B, D], keywords, graph_ids, collections) -> list of per-query results` is
-    normally `functools.partial(retriever.retrieve_batch, top_k=..., k_sem=..., k_lex=...)`.  It runs in the default
-    executor, so the event loop keeps accepting requests while the GPU works on the previous batch."""
+    normally `functools.partial(retriever.retrieve_batch, top_k=..., k_sem=..., k_lex=...)`.  It runs on ONE worker
+    thread owned by this front end: the event loop keeps accepting (and coalescing) requests while the GPU works on
+    the previous batch, and batches reach the engine strictly one after another — a libthr handle takes one thread at
+    a time (include/thr.h), two overlapping batches would share its scratch, counters and status word."""
 
     def __init__(self, batch_fn: Callable[..., List[Any]], max_batch: int = 256, max_wait_ms: float = 2.0):
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
+        from concurrent.futures import ThreadPoolExecutor
+        self._executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="thr-batch")
         self.batch_fn = batch_fn
         self.max_batch = int(max_batch)
         self.max_wait = float(max_wait_ms) / 1e3
@@ -74,7 +78,7 @@ class CoalescingFrontEnd:
             colls = [p.collection for p in batch]
             args = ([p.query for p in batch], torch.stack([p.vector.reshape(-1) for p in batch]),
                     [list(p.keywords) for p in batch], graph, colls if any(c is not None for c in colls) else None)
-            res = await asyncio.get_running_loop().run_in_executor(None, lambda: self.batch_fn(*args))
+            res = await asyncio.get_running_loop().run_in_executor(self._executor, lambda: self.batch_fn(*args))
             if len(res) != len(batch):
                 raise RuntimeError(f"batch function returned {len(res)} results for {len(batch)} requests")
             for p, r in zip(batch, res):
@@ -90,3 +94,6 @@ class CoalescingFrontEnd:
         self._flush()
         if self._inflight:
             await asyncio.gather(*list(self._inflight), return_exceptions=True)
+
+    def close(self) -> None:
+        self._executor.shutdown(wait=True)

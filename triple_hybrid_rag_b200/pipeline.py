@@ -171,32 +171,56 @@ class TripleHybridSearcher:
     # Signal arrays live in the last KiB of torch symmetric memory's signal pad (its own barriers use the front).
     _SIG_OFF = 8192
 
+    _PEER_MAX_STATES = 4   # symmetric buffers kept alive (one per (k_sem, k_lex) in use; least recently used goes)
+
     def _peer_state(self, B, k_sem, k_lex):
-        """Symmetric-memory buffers for the pushed exchange of this (B, k_sem, k_lex): two halves of G message
-        slots, mapped into every rank.  None when symmetric memory cannot be set up (then: NCCL all-gather)."""
-        key = ("peer", B, k_sem, k_lex)
+        """Symmetric-memory buffers for the pushed exchange: two halves of G message slots, mapped into every rank,
+        sized for the largest batch seen so far with these list depths (a smaller batch uses a prefix of each half:
+        the slot stride is the message size of the CURRENT batch on every rank).  None when the pushed exchange is not
+        in use.  Whether it is in use is decided COLLECTIVELY: every rank tries the local set-up, then the ranks
+        agree (all-reduce MIN of an ok flag) — if any rank failed, all of them take the NCCL all-gather, so the ranks
+        can never disagree about the path (a rank pushing while another waits in all_gather would hang)."""
+        import torch.distributed as dist
+        key = ("peer", k_sem, k_lex)
         st = self._offs.get(key)
-        if st is not None or key in self._offs:
+        nbytes = self.engine.exchange_msg_bytes(B, k_sem, k_lex)
+        if st is not None and st["cap"] >= nbytes:
+            st["nbytes"] = nbytes
+            st["used"] = self._peer_clock = getattr(self, "_peer_clock", 0) + 1
             return st
-        st = None
+        if st is None and key in self._offs:
+            return None                      # the ranks agreed on NCCL for these depths before
+        st, why = None, None
         if self.exchange != "nccl":
             try:
                 import torch.distributed._symmetric_memory as symm
                 eng = self.engine
-                nbytes = eng.exchange_msg_bytes(B, k_sem, k_lex)
-                buf = symm.empty(2 * self.world * nbytes, dtype=torch.uint8, device=eng.device)
+                cap = 1 << max(16, (nbytes - 1).bit_length())     # next power of two: regrowth is rare
+                buf = symm.empty(2 * self.world * cap, dtype=torch.uint8, device=eng.device)
                 hdl = symm.rendezvous(buf, self.group)
                 if hdl.signal_pad_size < self._SIG_OFF + 8 * self.world:
                     raise RuntimeError("signal pad too small")
-                st = {"buf": buf, "hdl": hdl, "nbytes": nbytes, "seq": 0,
+                st = {"buf": buf, "hdl": hdl, "cap": cap, "nbytes": nbytes, "seq": 0,
                       "done": torch.zeros((1,), dtype=torch.int32, device=eng.device),
                       "sig_ptr": int(hdl.signal_pad_ptrs[self.rank]) + self._SIG_OFF}
-                hdl.barrier()   # every rank's buffers and signal pads exist and are zero before the first push
             except Exception as e:  # no peer mapping on this system: the collective is NCCL's
-                self.exchange_fallback = f"{type(e).__name__}: {e}"
+                why = f"{type(e).__name__}: {e}"
                 st = None
         else:
-            self.exchange_fallback = "exchange='nccl' requested"
+            why = "exchange='nccl' requested"
+        ok = torch.tensor([1 if st is not None else 0], dtype=torch.int32, device=self.engine.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # the ranks agree on the path
+        if int(ok.item()) == 0:
+            if st is not None:
+                why = "set-up failed on another rank"
+            st = None
+            self.exchange_fallback = why
+        else:
+            st["hdl"].barrier()   # every rank's buffers and signal pads exist and are zero before the first push
+            st["used"] = self._peer_clock = getattr(self, "_peer_clock", 0) + 1
+            live = [k for k, v in self._offs.items() if isinstance(k, tuple) and k and k[0] == "peer" and v is not None]
+            if len(live) >= self._PEER_MAX_STATES:     # same order on every rank: the clocks advance in lock step
+                del self._offs[min(live, key=lambda k: self._offs[k]["used"])]
         self._offs[key] = st
         return st
 
@@ -220,7 +244,7 @@ class TripleHybridSearcher:
         st = self._peer_state(B, k_sem, k_lex)
         if st is not None:
             st["seq"] += 1
-            half = (st["seq"] & 1) * self.world * st["nbytes"]
+            half = (st["seq"] & 1) * self.world * st["cap"]
             hdl = st["hdl"]
             eng.exchange_push(d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt, int(hdl.buffer_ptrs_dev), half,
                               int(hdl.signal_pad_ptrs_dev), self._SIG_OFF, self.rank, self.world, st["seq"], st["done"])

@@ -320,6 +320,13 @@ class ResidentIndex:
         self._set_tags()
         return self
 
+    def _rows_first(self, text: str) -> int:
+        """Row of the first chunk whose text is `text` (-1: none)."""
+        for i, r in enumerate(self.rows):
+            if r.get("text", "") == text:
+                return i
+        return -1
+
     def row_dict(self, i: int, **extra) -> Dict[str, Any]:
         r = self.rows[i]
         d = {"child_id": r["child_id"], "parent_id": r["parent_id"], "document_id": r["document_id"],
@@ -530,7 +537,13 @@ class _GpuScoring:
         collections: per query, the collection its semantic and lexical hits must belong to (None: any)."""
         from .pipeline import TripleHybridSearcher
         eng, ix = self._need_engine(), self.index
-        s = TripleHybridSearcher(eng)
+        with eng.lock:     # a batch is several C-ABI calls on one handle: one thread at a time (engine.lock)
+            return self._retrieve_batch_locked(TripleHybridSearcher(eng), queries, query_vectors, keywords, graph_ids,
+                                               top_k, k_sem, k_lex, weights, collections)
+
+    def _retrieve_batch_locked(self, s, queries, query_vectors, keywords, graph_ids, top_k, k_sem, k_lex, weights,
+                               collections):
+        eng, ix = self.engine, self.index
         s.has_dense = s.has_bm25 = True
         B = len(queries)
         Q = query_vectors.to(torch.float32)
