@@ -24,6 +24,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "QPS (batch 256) triple-hybrid top-100 over 10M x 1536 chunks"
+METRIC_CFG5 = "QPS (batch 256) triple-hybrid top-100 + MaxSim rerank over 50M x 1024 chunks, sharded (BASELINE configs[4])"
 ALIGN = 16384  # shard boundaries (a multiple of the BM25 range size)
 BM25_BLK = 2048  # docs per BM25 range
 GEN_DOCS = 262144
@@ -40,9 +41,23 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--vocab", type=int, default=100_000)
-    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("THR_BENCH_CPU_SAMPLE", 262144)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="metric", choices=["metric", "cfg5"],
+                    help="metric: BASELINE.json's metric config (10M x 1536, dense + BM25 + RRF).  cfg5: BASELINE configs[4] — "
+                         "50M x 1024 sharded dense + BM25 + RRF + MaxSim rerank (needs >= 2 GPUs: 181 GB do not fit one)")
+    ap.add_argument("--rerank-top", type=int, default=100, help="cfg5: fused candidates reranked per query")
+    ap.add_argument("--tq", type=int, default=32, help="cfg5: query tokens")
+    ap.add_argument("--td", type=int, default=64, help="cfg5: tokens per chunk in the store (64 or 128)")
+    ap.add_argument("--store-rows", type=int, default=1 << 20,
+                    help="cfg5: rows of each rank's synthetic token store (chunk id -> row modulo this; a full store is "
+                         "16 KB per chunk, 800 GB at 50M chunks)")
+    a = ap.parse_args()
+    if a.workload == "cfg5":
+        if "THR_BENCH_CHUNKS" not in os.environ and a.chunks == 10_000_000:
+            a.chunks = 50_000_000
+        if "THR_BENCH_DIM" not in os.environ and a.dim == 1536:
+            a.dim = 1024
+    return a
 
 
 def peaks():
@@ -114,66 +129,129 @@ class ClockSampler:
 RUN_AHEAD = int(os.environ.get("THR_BENCH_RUN_AHEAD", "3"))
 
 
+def digest(*tensors) -> str:
+    """sha256 over the raw bytes of device tensors (ids, score BITS, counts): equal digests across N = 1/2/4/8 prove
+    that the sharded step returns exactly what the unsharded one does."""
+    import hashlib
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(t.detach().contiguous().cpu().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
 def make_config(args, world: int):
     N, D, B, k, V = args.chunks, args.dim, args.batch, args.k, args.vocab
-    return {"workload": f"triple-hybrid top-{k}: dense {N}x{D} bf16 + BM25 {N} docs V={V} (Zipf) + weighted RRF "
-                        f"1.0/0.8/0.7 with a synthetic 50-id graph list, batch {B}",
-            "chunks": N, "dim": D, "batch": B, "k": k, "channel_depths": [k, k, 50],
-            "parallelism": f"chunk-sharded x{world}" if world > 1 else "single GPU",
-            "l2": "inputs larger than L2 (per-rank corpus shard >> 126 MB); no explicit flush",
-            "rerank": "MaxSim (K4) is not part of this step; see tests and DESIGN.md"}
+    cfg = {"workload": f"triple-hybrid top-{k}: dense {N}x{D} bf16 + BM25 {N} docs V={V} (Zipf) + weighted RRF "
+                       f"1.0/0.8/0.7 with a synthetic 50-id graph list, batch {B}",
+           "chunks": N, "dim": D, "batch": B, "k": k, "channel_depths": [k, k, 50],
+           "parallelism": f"chunk-sharded x{world}" if world > 1 else "single GPU",
+           "l2": "inputs larger than L2 (per-rank corpus shard >> 126 MB); no explicit flush",
+           "rerank": "MaxSim (K4) is not part of the metric's step (BASELINE.json's metric names dense + BM25 + RRF); "
+                     "--workload cfg5 times the step with the rerank stage"}
+    if args.workload == "cfg5":
+        cfg["workload"] = ("BASELINE configs[4]: " + cfg["workload"] + f" + MaxSim rerank of the top {args.rerank_top} fused "
+                           f"candidates (Tq={args.tq}, Td={args.td}, d=128) + safety 0.6 / denoise 0.6, final top-5")
+        cfg["rerank"] = {"candidates": args.rerank_top, "Tq": args.tq, "Td": args.td, "d": 128,
+                         "token_store": f"synthetic, {args.store_rows} rows per rank, chunk id -> row modulo that "
+                                        "(a full store is 16 KB per chunk)",
+                         "exchange": "one all-reduce(MAX) of the [B, C] fp32 scores (NCCL)" if world > 1 else "none"}
+    return cfg
 
 
-def cpu_baseline(args, threads=None):
-    """CPU port on a bounded sample of the same workload; returns the cpu_baseline dict + QPS."""
+CPU_SHARD = 1 << 20   # chunks per CPU shard (a multiple of the generator blocks)
+
+
+def cpu_corpus(args, n_shards, threads=None):
+    """Shards [0, n_shards) of the SAME synthetic corpus for the CPU port (oracle/cpu_pipeline.py): generated block-wise
+    with torch (on the GPU when there is one — data preparation, outside every timed region), held in host memory as
+    fp32 rows + a scipy CSR matrix of fp32 BM25 impacts.  idf / avgdl are those of the shards that are held."""
     import numpy as np
+    import scipy.sparse as sp
     import torch
-    from oracle import bm25 as ob
     from oracle import cpu_pipeline as cp
     from triple_hybrid_rag_b200 import synth
     if threads:
         torch.set_num_threads(threads)
     cores = torch.get_num_threads()
-    ns = min(args.cpu_sample, args.chunks)
-    X = synth.dense_rows(0, ns, args.dim).float()
-    Q = synth.dense_queries(args.batch, args.dim, X[: max(1, ns // 8)]).float()
-    doc, term, tf, L = synth.bm25_block_coo(0, ns, V=args.vocab)
-    index = ob.CsrIndex.from_coo(doc.numpy(), term.numpy(), tf.numpy(), L.numpy(), args.vocab)
-    queries = synth.bm25_queries(args.batch, V=args.vocab)
-    g = np.random.default_rng(77).integers(0, ns, size=(args.batch, 50))
-    return X, Q, index, queries, g, ns, cores
+    gdev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    N, D, V = args.chunks, args.dim, args.vocab
+    n_held = min(N, n_shards * CPU_SHARD)
+    lens = [synth.bm25_doc_lens(gb, min(GEN_DOCS, n_held - gb * GEN_DOCS), device=gdev) for gb in range((n_held + GEN_DOCS - 1) // GEN_DOCS)]
+    avgdl = float(sum(int(l.sum().item()) for l in lens)) / n_held
+    shards, df = [], np.zeros(V, dtype=np.int64)
+    for s0 in range(0, n_held, CPU_SHARD):
+        s1 = min(n_held, s0 + CPU_SHARD)
+        X = synth.dense_rows(s0, s1, D, device=gdev).cpu().float()
+        indptr, terms, imps = [np.zeros(1, dtype=np.int64)], [], []
+        for gb in range(s0 // GEN_DOCS, (s1 + GEN_DOCS - 1) // GEN_DOCS):
+            rows = min(GEN_DOCS, N - gb * GEN_DOCS)
+            doc, term, tf, L = synth.bm25_block_coo(gb, rows, V=V, device=gdev)     # sorted by (doc, term)
+            keep = doc < (s1 - gb * GEN_DOCS)
+            doc, term, tf = doc[keep], term[keep], tf[keep]
+            tf64 = tf.to(torch.float64)
+            imp = (tf64 * 2.2 / (tf64 + 1.2 * (0.25 + 0.75 * L.to(torch.float64)[doc] / avgdl))).to(torch.float32)
+            cnt = torch.bincount(doc, minlength=min(rows, s1 - gb * GEN_DOCS))
+            indptr.append(indptr[-1][-1] + torch.cumsum(cnt, 0).cpu().numpy())
+            terms.append(term.to(torch.int32).cpu().numpy())
+            imps.append(imp.cpu().numpy())
+            df += torch.bincount(term, minlength=V).cpu().numpy()
+        # (doc, term)-sorted COO IS the CSC layout of W [V, n]: no sort needed; one conversion to CSR for the products
+        W = sp.csc_matrix((np.concatenate(imps), np.concatenate(terms), np.concatenate(indptr)), shape=(V, s1 - s0)).tocsr()
+        shards.append(cp.CpuShard(s0, X, W))
+    d = df.astype(np.float64)
+    idf = np.log(1.0 + (n_held - d + 0.5) / (d + 0.5)).astype(np.float32)
+    Q = synth.dense_queries(args.batch, D, shards[0].X[: max(1, shards[0].X.shape[0] // 8)].to(torch.bfloat16)).float()
+    queries = synth.bm25_queries(args.batch, V=V)
+    g = np.random.default_rng(77).integers(0, n_held, size=(args.batch, 50))
+    return {"shards": shards, "idf": idf, "Q": Q, "queries": queries, "graph": g, "held": n_held, "cores": cores}
 
 
-def cpu_time_step(args, state):
+def cpu_step(args, st, shards=None):
     from oracle import cpu_pipeline as cp
-    X, Q, index, queries, g, ns, cores = state
-    t = cp.step(Q, X, index, queries, g, args.k, args.k)
-    scale = args.chunks / ns
-    total = t["dense"] * scale + t["bm25"] * scale + t["fuse"]
-    return total, t
+    t = cp.step(st["Q"], shards or st["shards"], st["idf"], st["queries"], st["graph"], args.k, args.k, st["cores"])
+    return t["dense"] + t["bm25"] + t["fuse"], t
 
 
 def run_reference(args):
+    """The CPU port over the WHOLE corpus, streamed shard by shard from host memory — measured, not extrapolated:
+    `ms_per_step` is the wall time of one batch of 256 queries against every held shard.  If host memory cannot hold
+    the corpus (fp32 rows: 61 GB at 10M x 1536) the arm holds as many shards as fit and says so in `sample`; only then
+    is the dense + BM25 time scaled (by corpus / held)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # all the host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would otherwise leave the
-    # reference arm on one thread at N > 1
-    state = cpu_baseline(args, threads=len(os.sched_getaffinity(0)))
-    ns, cores = state[5], state[6]
-    for _ in range(min(args.warmup, 1)):
-        cpu_time_step(args, state)
-    steps = max(1, min(args.steps, 5))
-    tot = []
-    for _ in range(steps):
-        t, _parts = cpu_time_step(args, state)
+    t_setup = time.time()
+    threads = len(os.sched_getaffinity(0))   # torchrun exports OMP_NUM_THREADS=1: take every core this process may use
+    n_sh = (args.chunks + CPU_SHARD - 1) // CPU_SHARD
+    try:
+        avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
+        per = CPU_SHARD * (args.dim * 4 + 150 * 8) * 1.3
+        n_sh = max(1, min(n_sh, int(0.6 * avail / per)))
+    except Exception:
+        pass
+    st = cpu_corpus(args, n_sh, threads=threads)
+    held, cores = st["held"], st["cores"]
+    cpu_step(args, st, st["shards"][:1])                    # warm-up: one shard (thread pools, BLAS buffers)
+    budget = float(os.environ.get("THR_BENCH_CPU_BUDGET_S", "150"))
+    tot, parts = [], None
+    t_first, parts = cpu_step(args, st)
+    tot.append(t_first)
+    steps = max(1, min(args.steps, int(budget // max(t_first, 1e-3))))
+    for _ in range(steps - 1):
+        t, parts = cpu_step(args, st)
         tot.append(t)
-    sec = statistics.median(tot)
+    scale = args.chunks / held
+    sec = statistics.median(tot) if scale == 1.0 else statistics.median(tot) * scale
     qps = args.batch / sec
-    sample = (f"each step runs the batch of {args.batch} queries over the first {ns} chunks/docs of the corpus and is "
-              f"scaled x{args.chunks / ns:.1f} (dense and BM25 are linear in corpus size); fusion unscaled")
+    how = (f"each step is the batch of {args.batch} queries against ALL {args.chunks} chunks/docs, streamed as "
+           f"{len(st['shards'])} host-resident shards (measured, not extrapolated)") if scale == 1.0 else (
+           f"host memory holds {held} of {args.chunks} chunks/docs ({len(st['shards'])} shards): each step is the batch of "
+           f"{args.batch} queries against those, scaled x{scale:.2f}")
+    sample = (f"{how}; {steps} timed step(s) within a {budget:.0f} s budget; stage seconds of the last step: dense "
+              f"{parts['dense']:.2f} (torch fp32 matmul + topk), bm25 {parts['bm25']:.2f} (scipy.sparse), fuse {parts['fuse']:.3f} "
+              f"({parts['fusion_code']}); setup {time.time() - t_setup - sum(tot):.0f} s")
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(make_config(args, 1), parallelism=f"host CPU, {cores} threads"),
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
@@ -206,6 +284,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     N, D, B, k, V = args.chunks, args.dim, args.batch, args.k, args.vocab
+    rerank = args.workload == "cfg5"
+    if rerank:
+        need = (N * D * 2 + N * 150 * 8 + (N // BM25_BLK) * V * 8) / world + args.store_rows * args.td * 256
+        have = torch.cuda.get_device_properties(dev).total_memory
+        if need > 0.97 * have:
+            raise SystemExit(f"cfg5 at {N} chunks needs about {need / 1e9:.0f} GB per GPU on {world} GPU(s); "
+                             f"{have / 1e9:.0f} GB available — use more GPUs (--gpus under torchrun)")
 
     eng = Engine(dev)
     searcher = TripleHybridSearcher(eng, group)
@@ -258,7 +343,28 @@ def main():
     out0 = searcher.search(Q, q_terms, q_off, None, k_sem=k, k_lex=k, top_k=k)
     eng.sync()
     graph = synth.graph_lists(out0.sem_ids, out0.lex_ids, N, length=50).to(dev)
+    Qtok = None
+    if rerank:   # late-interaction stage: per-rank synthetic token store + the batch's query tokens (replicated)
+        rows = min(args.store_rows, hi - lo)
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(99 + 1000 * rank)
+        store = torch.empty((rows, args.td, 128), dtype=torch.bfloat16, device=dev)
+        for s0 in range(0, rows, 65536):
+            x = torch.randn((min(65536, rows - s0), args.td, 128), generator=gq, dtype=torch.float32, device=dev)
+            store[s0:s0 + x.shape[0]] = (x / x.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+        searcher.set_token_store(store, lo, hi, period=rows)
+        gq.manual_seed(98)
+        Qtok = torch.randn((B, args.tq, 128), generator=gq, dtype=torch.float32, device=dev)
+        Qtok = (Qtok / Qtok.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+        if world > 1:
+            dist.broadcast(Qtok, 0, group=group)
     setup_s = time.time() - t_setup
+
+    def one_step():
+        o = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+        if rerank:   # reference defaults: threshold 0.6, alpha 0.6, final top-5 (src/voice_agent/config.py:305-314)
+            o = searcher.rerank(o, Qtok, args.rerank_top, 0.6, 0.6, 5)
+        return o
 
     def barrier():
         if world > 1:
@@ -281,7 +387,7 @@ def main():
         # 40-80 ms on every rank at once.
         evs, keep = [], None
         for i in range(n):
-            keep = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+            keep = one_step()
             e = torch.cuda.Event()
             e.record()
             evs.append(e)
@@ -318,7 +424,7 @@ def main():
     ev0.record()
     host_t = [time.perf_counter()]
     for i in range(args.steps):
-        out = searcher.search(Q, q_terms, q_off, graph, k_sem=k, k_lex=k, top_k=k)
+        out = one_step()
         step_ev[i].record()
         host_t.append(time.perf_counter())
         if i >= RUN_AHEAD:  # the host stays at most RUN_AHEAD steps ahead of the device (the GPU never runs dry)
@@ -341,17 +447,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     ms_step = float(t.item()) / args.steps
     qps = B / (ms_step * 1e-3)
+    # what the LAST timed step returned: digests (identical on every rank and for every N) and K1's exactness
+    # certificate (each rank certifies its own shard: the minimum over queries and ranks must clear the bound)
+    from triple_hybrid_rag_b200.retriever import dense_error_bound
+    digests = {"result_digest": digest(out.ids, out.rrf, out.count),
+               "sem_digest": digest(out.sem_ids, out.sem_scores),
+               "lex_digest": digest(out.lex_ids, out.lex_scores, out.lex_count)}
+    if rerank:
+        digests["rerank_digest"] = digest(out.rr_ids, out.rr_score, out.rr_keep, out.refused, out.max_score)
+    qn = float(Q.float().norm(dim=1).max().item())
+    xn = float(X[: min(hi - lo, 1 << 20)].float().norm(dim=1).max().item())
+    cert_bound = dense_error_bound(D, qn, xn)
+    min_gap = out.gap.min().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(min_gap, op=dist.ReduceOp.MIN, group=group)
+    min_gap = float(min_gap.item())
 
     # ---- end to end: pinned host inputs -> search -> pinned host outputs, every step ----
     hQ, hT, hO, hG = (x.cpu().pin_memory() for x in (Q, q_terms, q_off, graph))
+    rr_kw = {}
+    if rerank:
+        rr_kw = {"Qtok": Qtok.cpu().pin_memory(), "rerank": (args.rerank_top, 0.6, 0.6, 5)}
     for _ in range(2):
-        searcher.search_host(hQ, hT, hO, hG, k_sem=k, k_lex=k, top_k=k)
+        searcher.search_host(hQ, hT, hO, hG, k_sem=k, k_lex=k, top_k=k, **rr_kw)
     lat = []
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         s0 = time.perf_counter()
-        _, _, _, h2d, d2h = searcher.search_host(hQ, hT, hO, hG, k_sem=k, k_lex=k, top_k=k)
+        _, _, _, h2d, d2h = searcher.search_host(hQ, hT, hO, hG, k_sem=k, k_lex=k, top_k=k, **rr_kw)
         lat.append(time.perf_counter() - s0)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -383,7 +507,7 @@ def main():
     burst, sustained, hbm, which = peaks()
     traffic = {}
     try:  # DRAM bytes per launch from the committed ncu capture of this exact configuration, else null
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        tj = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
         c = tj["config"]
         if (c["chunks"], c["dim"], c["batch"], c["n_gpus"]) == (N, D, B, world):
             traffic = tj
@@ -397,13 +521,18 @@ def main():
     stages = {n: round(ms / max(c, 1), 4) for n, (ms, c) in prof.items()}
     bm25_bytes = index.algorithmic_bytes(queries)
     bm25_ms = stages.get("bm25", 0.0)
+    maxsim_ms = stages.get("maxsim", 0.0)
     line = {
-        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC_CFG5 if rerank else METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {**make_config(args, world), "exchange": searcher.exchange_mode},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        **digests,
+        "dense_certificate": {"min_gap": min_gap, "bound": cert_bound, "certified": bool(min_gap > cert_bound),
+                              "meaning": "min over queries and shards of (exact k-th score) - (best tensor-core score not "
+                                         "re-scored in fp64); above the fp32 accumulation bound D*2^-23*|q|*|x| the top-k ids are exact"},
         "clocks": clk,
         "latency": {"p50_ms_batch256_e2e": statistics.median(lat) * 1e3, "p50_ms_batch1_e2e": statistics.median(lat1) * 1e3},
         "step_ms": {"p50": statistics.median(per_step), "min": min(per_step), "max": max(per_step),
@@ -419,22 +548,34 @@ def main():
                      "hbm_gbs": x_bytes / (dense_avg * 1e-3) / 1e9 if dense_avg > 0 else 0.0,
                      "hbm_frac": (x_bytes / (dense_avg * 1e-3) / 1e9) / hbm if dense_avg > 0 else None,
                      "launch_ms": dense_avg, "launches": dense_n},
-        "bm25_roofline": {"kernel": "bm25_span_kernel", "bound": "hbm", "algorithmic_bytes": bm25_bytes,
+        "bm25_roofline": {"kernel": "bm25_range_kernel", "bound": "hbm", "algorithmic_bytes": bm25_bytes,
                           "achieved": bm25_bytes / (bm25_ms * 1e-3) / 1e9 if bm25_ms > 0 else 0.0, "peak": hbm,
                           "unit": "GB/s", "frac": (bm25_bytes / (bm25_ms * 1e-3) / 1e9) / hbm if bm25_ms > 0 else None,
-                          "traffic": traffic.get("bm25_span_kernel", {}).get("dram_bytes_per_launch")},
+                          "traffic": traffic.get("bm25_range_kernel", {}).get("dram_bytes_per_launch")},
         "setup_s": round(setup_s, 1),
     }
+    if rerank:   # K4 against HBM: the token rows of the candidates THIS rank owns (about B*C/world) are read once
+        owned = int((out.ids[:, :args.rerank_top] >= lo).logical_and(out.ids[:, :args.rerank_top] < hi).sum().item())
+        ms_bytes = owned * args.td * 128 * 2
+        line["maxsim_roofline"] = {"kernel": "maxsim_kernel", "bound": "hbm", "algorithmic_bytes": ms_bytes,
+                                   "candidates_scored_on_rank0": owned, "launch_ms": maxsim_ms,
+                                   "achieved": ms_bytes / (maxsim_ms * 1e-3) / 1e9 if maxsim_ms > 0 else 0.0, "peak": hbm,
+                                   "unit": "GB/s", "frac": (ms_bytes / (maxsim_ms * 1e-3) / 1e9) / hbm if maxsim_ms > 0 else None,
+                                   "note": "tens of microseconds per launch: latency-bound at this candidate count"}
     if world == 1 and not args.no_cpu_baseline:
-        try:
-            state = cpu_baseline(args)
-            cpu_time_step(args, state)
-            sec, parts = cpu_time_step(args, state)
-            ns, cores = state[5], state[6]
+        try:   # bounded sample: ONE shard of the same corpus (about 10-20 s of CPU work), dense + BM25 scaled to the corpus
+            del X
+            torch.cuda.empty_cache()
+            st = cpu_corpus(args, 1)
+            cpu_step(args, st)
+            sec_s, parts = cpu_step(args, st)
+            held, cores = st["held"], st["cores"]
+            sec = (parts["dense"] + parts["bm25"]) * (N / held) + parts["fuse"]
             line["cpu_baseline"] = {"value": B / sec, "unit": "queries/s", "cores": cores, "kind": "port",
-                                    "sample": f"batch {B} over the first {ns} chunks/docs, dense+BM25 scaled x{N / ns:.1f}; "
-                                              f"stage seconds on the sample: {{'dense': {parts['dense']:.3f}, "
-                                              f"'bm25': {parts['bm25']:.3f}, 'fuse': {parts['fuse']:.3f}}}"}
+                                    "sample": f"batch {B} over the first {held} chunks/docs of the corpus (one measured pass: "
+                                              f"dense {parts['dense']:.2f} s torch fp32 matmul + topk, bm25 {parts['bm25']:.2f} s "
+                                              f"scipy.sparse, fuse {parts['fuse']:.3f} s {parts['fusion_code']}); dense + BM25 "
+                                              f"scaled x{N / held:.1f} to the corpus; `--impl reference` measures the whole corpus"}
         except Exception as e:  # the baseline is a reported extra; never lose the GPU numbers over it
             line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": None, "kind": "port",
                                     "sample": f"failed: {e!r}"}

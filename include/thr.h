@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 7
+#define THR_ABI_VERSION 8
 
 enum {
   THR_OK = 0,
@@ -75,7 +75,8 @@ enum {
   THR_PROF_DENSE_SCORE = 0, THR_PROF_DENSE_FINALIZE = 1, THR_PROF_BM25 = 2, THR_PROF_FUSE = 3,
   THR_PROF_MAXSIM = 4, THR_PROF_MERGE = 5, THR_PROF_SAFETY = 6, THR_PROF_BM25_PREP = 7,
   THR_PROF_DENSE_SEED = 8, /* seed pass of thr_dense_topk: prefix scoring + threshold select (two launches) */
-  THR_PROF_SLOTS = 9
+  THR_PROF_RERANK = 9,     /* thr_rerank_rows + thr_rerank_finish around thr_maxsim */
+  THR_PROF_SLOTS = 10
 };
 int thr_prof_enable(thr_handle* h, int on);
 int thr_prof_reset(thr_handle* h);
@@ -243,6 +244,32 @@ int thr_safety(thr_handle* h, int B, const int32_t* off, const double* rerank,
 int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int Tq, int d,
                const void* Dtok, const int32_t* d_len, int64_t n_docs, int Td,
                const int64_t* cand, int C, float* out, void* stream);
+
+/* The batched rerank stage around thr_maxsim — RAG2Retriever.retrieve steps 4-6, src/voice_agent/rag2/retrieval.py:175-191,
+ * for B queries at once (the reference runs them one query at a time in Python).
+ *
+ * thr_rerank_rows: the first C candidates of each fused list -> rows of THIS rank's token store.
+ *   ids [B, stride] int64 fused ids (-1 padded), count [B]; a candidate whose id lies in [id_lo, id_hi) (the chunk-id
+ *   range this rank owns) maps to row (id - id_lo), taken modulo `period` when period > 0 (a synthetic store that
+ *   repeats); every other slot maps to -1, which thr_maxsim scores -inf.  rows [B, C] int64.
+ * With a sharded corpus the ranks then exchange the [B, C] float scores with one all-reduce(MAX) (exactly one rank owns
+ * a candidate); single GPU: no exchange.
+ *
+ * thr_rerank_finish: `_rerank`'s ordering and `_apply_safety` (retrieval.py:455, :461-495) on the merged scores.
+ *   raw [B, C] float: MaxSim sums, -inf where the candidate was not scored.  Per query, over its first
+ *   n = min(count, C) candidates:  rerank_score = min(1, max(0, 0.5 * (raw / Tq + 1))) in fp64 (none if raw == -inf);
+ *   order = sorted(key = rerank_score or 0, reverse = True), stable;  s_i = rerank_score or rrf_score;
+ *   max_score = max s_i; refused = max_score < threshold (n == 0: refused, 0.0);
+ *   keep_i = !refused && s_i >= alpha * max_score && fewer than top_k kept before i.
+ *   Outputs in the reranked order, [B, C]: out_ids (-1 padded), out_rerank (-1 where none), out_rrf, out_keep;
+ *   out_n [B], refused [B] uint8, max_score [B].  1 <= C <= 256.
+ */
+int thr_rerank_rows(thr_handle* h, const int64_t* ids, const int32_t* count, int B, int C, int stride,
+                    int64_t id_lo, int64_t id_hi, int64_t period, int64_t* rows, void* stream);
+int thr_rerank_finish(thr_handle* h, int B, int C, int stride, const int64_t* ids, const double* rrf,
+                      const int32_t* count, const float* raw, int Tq, double threshold, double alpha, int top_k,
+                      int64_t* out_ids, double* out_rerank, double* out_rrf, uint8_t* out_keep, int32_t* out_n,
+                      uint8_t* refused, double* max_score, void* stream);
 
 /* ---- K5: merge of per-shard top-k lists (consumes the all-gather buffer) ----------
  * scores [G,B,k_in] double, ids [G,B,k_in] int64, counts [G,B] int32 (valid prefix per list).

@@ -10,5 +10,5 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 mkdir -p build/var
 $NVCC $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $flags -Xptxas -v -c bm25.cu -o build/var/bm25_$name.o 2> build/var/bm25_$name.log
 grep -A2 "range_kernelILi2048ELb0" build/var/bm25_$name.log | grep -E "registers|spill" | head -2
-$NVCC $ARCH -shared -o ../lib/libthr_$name.so build/api.o build/fuse.o build/dense_topk.o build/var/bm25_$name.o build/maxsim.o -lcudart
+$NVCC $ARCH -shared -o ../lib/libthr_$name.so build/api.o build/fuse.o build/dense_topk.o build/var/bm25_$name.o build/maxsim.o build/rerank.o -lcudart
 echo built libthr_$name.so

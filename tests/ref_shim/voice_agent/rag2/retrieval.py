@@ -22,7 +22,7 @@ def _shared_engine() -> Engine:
 class RAG2Retriever(_r.StandaloneGpuRAG2Retriever):
     def __init__(self, org_id, embedder=None, query_planner=None, graph_enabled=False, **kw):
         kw.setdefault("engine", _shared_engine())
-        super().__init__(org_id, embedder=embedder or MagicMock(), query_planner=query_planner or MagicMock(),
+        super().__init__(org_id, embedder=embedder or MagicMock(), query_planner=query_planner,
                          graph_enabled=graph_enabled, **kw)
 
 

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     __syncthreads();
     const int unit = vsh->unit;
     if (unit < 0) break;
-    const int q = a.units[unit].q, r0 = a.units[unit].r0, r1 = a.units[unit].r1;
+    const int q = a.units[unit].q, r1 = a.units[unit].r1;
     const int qlo = a.q_off[q];
     const int nt = min(a.q_off[q + 1] - qlo, kMaxTerms);   // longer queries are reported by bm25_cost_kernel
     int term = -1;

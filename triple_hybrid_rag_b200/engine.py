@@ -260,6 +260,42 @@ class Engine:
                                          Td, _ptr(cand), Cc, _ptr(out), self._stream()))
         return out
 
+    # -- the batched rerank stage around K4 ---------------------------------------------------
+    def rerank_rows(self, ids: torch.Tensor, count: torch.Tensor, C: int, id_lo: int, id_hi: int, period: int = 0
+                    ) -> torch.Tensor:
+        """Fused ids [B, stride] (+ count [B]) -> rows [B, C] of this rank's token store (-1: not owned / padding)."""
+        ids = self._dev(ids, torch.int64, "ids")
+        count = self._dev(count, torch.int32, "count")
+        B, stride = ids.shape
+        rows = torch.empty((B, C), dtype=torch.int64, device=self.device)
+        self._check(self._lib.thr_rerank_rows(self._h, _ptr(ids), _ptr(count), B, C, stride, id_lo, id_hi, period,
+                                              _ptr(rows), self._stream()))
+        return rows
+
+    def rerank_finish(self, ids: torch.Tensor, rrf: torch.Tensor, count: torch.Tensor, raw: torch.Tensor, Tq: int,
+                      threshold: float, alpha: float, top_k: int):
+        """`_rerank` ordering + `_apply_safety` for B queries (include/thr.h: thr_rerank_finish).
+        -> ids [B,C], rerank [B,C] f64 (-1: none), rrf [B,C], keep [B,C] u8, n [B], refused [B] u8, max_score [B] f64."""
+        ids = self._dev(ids, torch.int64, "ids")
+        rrf = self._dev(rrf, torch.float64, "rrf")
+        count = self._dev(count, torch.int32, "count")
+        raw = self._dev(raw, torch.float32, "raw")
+        B, stride = ids.shape
+        C = raw.shape[1]
+        dev = self.device
+        o_ids = torch.empty((B, C), dtype=torch.int64, device=dev)
+        o_rr = torch.empty((B, C), dtype=torch.float64, device=dev)
+        o_rrf = torch.empty((B, C), dtype=torch.float64, device=dev)
+        o_keep = torch.empty((B, C), dtype=torch.uint8, device=dev)
+        o_n = torch.empty((B,), dtype=torch.int32, device=dev)
+        o_ref = torch.empty((B,), dtype=torch.uint8, device=dev)
+        o_mx = torch.empty((B,), dtype=torch.float64, device=dev)
+        self._check(self._lib.thr_rerank_finish(self._h, B, C, stride, _ptr(ids), _ptr(rrf), _ptr(count), _ptr(raw), int(Tq),
+                                                float(threshold), float(alpha), int(top_k), _ptr(o_ids), _ptr(o_rr),
+                                                _ptr(o_rrf), _ptr(o_keep), _ptr(o_n), _ptr(o_ref), _ptr(o_mx),
+                                                self._stream()))
+        return o_ids, o_rr, o_rrf, o_keep, o_n, o_ref, o_mx
+
     # -- K5 merge ---------------------------------------------------------------------------
     def merge_topk(self, scores: torch.Tensor, ids: torch.Tensor, counts: Optional[torch.Tensor], k_out: int):
         """scores [G,B,k] f64, ids [G,B,k] i64, counts [G,B] i32 -> scores [B,k_out], ids [B,k_out], count [B]."""

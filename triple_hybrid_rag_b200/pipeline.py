@@ -87,6 +87,14 @@ class SearchOutput:
     lex_scores: torch.Tensor
     lex_count: torch.Tensor
     gap: Optional[torch.Tensor] = None  # dense exactness certificate (local shard)
+    # rerank stage (when search() was given query tokens): the first C fused candidates in the reranked order
+    rr_ids: Optional[torch.Tensor] = None      # [B, C] int64, -1 padded
+    rr_score: Optional[torch.Tensor] = None    # [B, C] float64 rerank_score in [0, 1] (-1: none)
+    rr_rrf: Optional[torch.Tensor] = None      # [B, C] float64
+    rr_keep: Optional[torch.Tensor] = None     # [B, C] uint8: survives _apply_safety
+    rr_n: Optional[torch.Tensor] = None        # [B] int32
+    refused: Optional[torch.Tensor] = None     # [B] uint8
+    max_score: Optional[torch.Tensor] = None   # [B] float64
 
 
 class TripleHybridSearcher:
@@ -125,6 +133,31 @@ class TripleHybridSearcher:
         self.bm25 = d
         self.engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V, id_base=id_base)
         self.has_bm25 = True
+
+    def set_token_store(self, store: torch.Tensor, id_lo: int, id_hi: int, period: int = 0,
+                        lens: Optional[torch.Tensor] = None):
+        """This rank's late-interaction token store for the rerank stage: store [rows, Td, 128] bf16 holds the token
+        embeddings of the chunks [id_lo, id_hi) this rank owns, chunk id -> row (id - id_lo), modulo `period` when
+        period > 0 (synthetic stores that repeat; period == rows then)."""
+        self.tok_store = self.engine._dev(store, torch.bfloat16, "token store")
+        self.tok_lens = None if lens is None else self.engine._dev(lens, torch.int32, "token lens")
+        self.tok_lo, self.tok_hi, self.tok_period = int(id_lo), int(id_hi), int(period)
+
+    def rerank(self, out: "SearchOutput", Qtok: torch.Tensor, C: int, threshold: float, alpha: float, final_top_k: int,
+               q_len: Optional[torch.Tensor] = None) -> "SearchOutput":
+        """The rerank stage on a fused result (reference: retrieval.py:175-191, batched): the first C candidates of
+        every query are scored with MaxSim (K4) on the rank that owns their chunk, the [B, C] scores are exchanged with
+        ONE all-reduce(MAX) when the corpus is sharded (a candidate is scored -inf everywhere but on its owner), and
+        thr_rerank_finish orders by rerank score and applies the safety threshold / denoise on every rank."""
+        eng = self.engine
+        rows = eng.rerank_rows(out.ids, out.count, C, self.tok_lo, self.tok_hi, self.tok_period)
+        raw = eng.maxsim(Qtok, self.tok_store, rows, q_len=q_len, d_len=self.tok_lens)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(raw, op=dist.ReduceOp.MAX, group=self.group)
+        (out.rr_ids, out.rr_score, out.rr_rrf, out.rr_keep, out.rr_n, out.refused, out.max_score) = eng.rerank_finish(
+            out.ids, out.rrf, out.count, raw, Qtok.shape[1], threshold, alpha, final_top_k)
+        return out
 
     # ---- one batch, device tensors in / out ------------------------------------------------
     def search(self, Q: torch.Tensor, q_terms: torch.Tensor, q_off: torch.Tensor,
@@ -266,19 +299,26 @@ class TripleHybridSearcher:
         return buf
 
     def search_host(self, Q: torch.Tensor, q_terms: torch.Tensor, q_off: torch.Tensor,
-                    graph_ids: Optional[torch.Tensor], **kw):
+                    graph_ids: Optional[torch.Tensor], Qtok: Optional[torch.Tensor] = None, rerank=None, **kw):
         """Inputs are pinned CPU tensors; results come back as pinned CPU tensors.  Every call copies
-        the inputs host->device and the fused result device->host on the current stream and waits
-        for it.  Returns (ids, rrf, count, h2d_bytes, d2h_bytes)."""
+        the inputs host->device and the result device->host on the current stream and waits
+        for it.  Returns (ids, rrf, count, h2d_bytes, d2h_bytes); with Qtok (pinned [B, Tq, 128] bf16) and
+        rerank = (C, threshold, alpha, final_top_k) the rerank stage runs too and ids / rrf / count are the reranked
+        ids, rerank scores and keep flags (the refused flags and max scores travel back as well)."""
         dev = self.engine.device
-        ins = [Q, q_terms, q_off] + ([graph_ids] if graph_ids is not None else [])
+        ins = [Q, q_terms, q_off] + ([graph_ids] if graph_ids is not None else []) + ([Qtok] if Qtok is not None else [])
         dv = [t.to(dev, non_blocking=True) for t in ins]
         out = self.search(dv[0], dv[1], dv[2], dv[3] if graph_ids is not None else None, **kw)
-        h_ids, h_rrf, h_cnt = self._pin("ids", out.ids), self._pin("rrf", out.rrf), self._pin("cnt", out.count)
-        h_ids.copy_(out.ids, non_blocking=True)
-        h_rrf.copy_(out.rrf, non_blocking=True)
-        h_cnt.copy_(out.count, non_blocking=True)
+        res = (out.ids, out.rrf, out.count)
+        extra = ()
+        if Qtok is not None:
+            out = self.rerank(out, dv[-1], *rerank)
+            res = (out.rr_ids, out.rr_score, out.rr_keep)
+            extra = (out.refused, out.max_score)
+        host = [self._pin(f"o{i}", t) for i, t in enumerate(res + extra)]
+        for h_, t in zip(host, res + extra):
+            h_.copy_(t, non_blocking=True)
         self.engine.sync()
         h2d = sum(t.numel() * t.element_size() for t in ins)
-        d2h = sum(t.numel() * t.element_size() for t in (h_ids, h_rrf, h_cnt))
-        return h_ids, h_rrf, h_cnt, h2d, d2h
+        d2h = sum(t.numel() * t.element_size() for t in host)
+        return host[0], host[1], host[2], h2d, d2h

@@ -482,8 +482,9 @@ class _GpuScoring:
         return rr
 
     async def _rerank_batch_native(self, query: str, documents: List[str]) -> List[float]:
-        """Kept for round-1 callers: `documents` are child ids here.  The reference-shaped entry (texts in, scores
-        out) is GpuMaxSimReranker._rerank_batch_native."""
+        """What _rerank calls: `documents` are the candidates' CHILD IDS here (the row of the token store is known
+        from the id, no text look-up).  The reference-shaped entry (texts in, scores out) is
+        GpuMaxSimReranker._rerank_batch_native."""
         self._need_engine()
         return self.maxsim_reranker.score_rows(query, [self.index.id_of.get(d, -1) for d in documents])
 
@@ -495,9 +496,7 @@ class _GpuScoring:
         if not candidates:
             return []
         try:
-            self._need_engine()
-            rows = [self.index.id_of.get(c.child_id, -1) for c in candidates]
-            scores = self.maxsim_reranker.score_rows(query, rows)
+            scores = await self._rerank_batch_native(query, [c.child_id for c in candidates])
             for c, s in zip(candidates, scores):
                 c.rerank_score = s
             return sorted(candidates, key=lambda c: c.rerank_score or 0, reverse=True)
@@ -582,6 +581,22 @@ class _GpuScoring:
         return res
 
 
+class FallbackQueryPlanner:
+    """The plan the reference's QueryPlanner returns when its LLM call fails (src/voice_agent/rag2/query_planner.py:
+    178-187): keywords = the query's words, semantic text = the query, default depths.  Query planning itself is an
+    LLM call and stays outside the path; this is what a retriever built without a planner uses."""
+
+    def __init__(self, settings=None):
+        self._cfg = settings or SETTINGS
+
+    def plan(self, query: str, collection: Optional[str] = None) -> QueryPlan:
+        return QueryPlan(original_query=query, keywords=query.split(), semantic_query_text=query,
+                         lexical_top_k=self._cfg.rag2_lexical_top_k, semantic_top_k=self._cfg.rag2_semantic_top_k)
+
+    async def plan_async(self, query: str, collection: Optional[str] = None) -> QueryPlan:
+        return self.plan(query, collection)
+
+
 class StandaloneGpuRAG2Retriever(_GpuScoring):
     """Same call surface as the reference's RAG2Retriever (retrieval.py:66-495), with retrieve() and
     _retrieve_candidates() restated here because the reference package is not importable."""
@@ -597,7 +612,7 @@ class StandaloneGpuRAG2Retriever(_GpuScoring):
         match, the reference's `tsv @@ plainto_tsquery` (20260114_rag2_schema.sql:369); "any" = plain BM25 (OR)."""
         self.org_id = org_id
         self.embedder = embedder
-        self.query_planner = query_planner
+        self.query_planner = query_planner or FallbackQueryPlanner(self._cfg)   # the reference: get_query_planner()
         self.graph_enabled = graph_enabled and self._cfg.rag2_graph_enabled
         self._gpu_init(index, engine, graph_search, token_encoder, lexical_match)
 
