@@ -20,14 +20,29 @@ X = synth.dense_rows(0, N, D)
 Q = synth.dense_queries(B, D, X[: N // 8]).to(dev)
 qt, qo = pack_queries(synth.bm25_queries(B, V=V, min_rank=50), dev)
 graph = torch.randint(0, N, (B, 50), generator=torch.Generator().manual_seed(7)).to(dev)
+# rerank stage: a token store over the whole corpus (Td = 64), each rank holding the rows of its own chunks
+gt = torch.Generator().manual_seed(5)
+store = torch.randn((N // 8, 64, 128), generator=gt)
+store = (store / store.norm(dim=-1, keepdim=True)).to(torch.bfloat16)      # chunk id -> row id % (N // 8), on every rank
+Qtok = torch.randn((B, 32, 128), generator=gt)
+Qtok = (Qtok / Qtok.norm(dim=-1, keepdim=True)).to(torch.bfloat16).to(dev)
+P = N // 8
+def tup(o):
+    return (o.ids.cpu(), o.rrf.cpu(), o.count.cpu(), o.sem_ids.cpu(), o.lex_ids.cpu(), o.lex_scores.cpu(),
+            o.rr_ids.cpu(), o.rr_score.cpu(), o.rr_keep.cpu(), o.refused.cpu(), o.max_score.cpu())
 outs = {}
 for mode in ("peer", "nccl"):
     s = TripleHybridSearcher(eng, group=dist.group.WORLD, exchange=mode)
     s.set_dense(X[lo:hi].to(dev), id_base=lo); s.set_bm25(loc, id_base=lo)
-    for it in range(5):   # several steps: both buffer halves and growing sequence numbers
+    # shard boundaries are multiples of 16384 and P = 50000 is not: the local store is the rows (lo + j) % P for j < P
+    s.set_token_store(store[(torch.arange(P) + lo) % P].to(dev).contiguous(), lo, hi, period=P)
+    for it in range(5):   # several steps: both buffer halves and growing sequence numbers; a smaller batch in between
+        if it == 2:
+            s.search(Q[:40], *pack_queries(synth.bm25_queries(B, V=V, min_rank=50)[:40], dev), graph[:40], k_sem=k, k_lex=k, top_k=k)
         o = s.search(Q, qt, qo, graph, k_sem=k, k_lex=k, top_k=k)
+        o = s.rerank(o, Qtok, 60, 0.5, 0.9, 10)
     eng.sync()
-    outs[mode] = (o.ids.cpu(), o.rrf.cpu(), o.count.cpu(), o.sem_ids.cpu(), o.lex_ids.cpu(), o.lex_scores.cpu())
+    outs[mode] = tup(o)
     if rank == 0:
         print(mode, "->", s.exchange_mode, flush=True)
 same = all(torch.equal(a, b) for a, b in zip(outs["peer"], outs["nccl"]))
@@ -35,12 +50,14 @@ ok = torch.tensor([int(same)], device=dev)
 if rank == 0:   # unsharded reference on the same GPU
     s1 = TripleHybridSearcher(eng)
     s1.set_dense(X.to(dev)); s1.set_bm25(full)
+    s1.set_token_store(store.to(dev), 0, N, period=P)
     o = s1.search(Q, qt, qo, graph, k_sem=k, k_lex=k, top_k=k)
+    o = s1.rerank(o, Qtok, 60, 0.5, 0.9, 10)
     eng.sync()
-    ref = (o.ids.cpu(), o.rrf.cpu(), o.count.cpu(), o.sem_ids.cpu(), o.lex_ids.cpu(), o.lex_scores.cpu())
+    ref = tup(o)
     ok[0] = int(same and all(torch.equal(a, b) for a, b in zip(outs["peer"], ref)))
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("exchange check:", "OK — pushed == NCCL == unsharded, bit for bit" if int(ok) else "MISMATCH", flush=True)
+    print(f"exchange check (world {world}):", "OK — pushed == NCCL == unsharded, bit for bit, fused lists and reranked lists" if int(ok) else "MISMATCH", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if int(ok) else 1)

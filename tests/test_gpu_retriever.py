@@ -362,3 +362,56 @@ def test_no_engine_fails_loudly():
     r = GpuRAG2Retriever(org_id="t")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         r._fuse_rrf([cand(1, l=1)], {})
+
+
+def test_coalesced_tool_boundary_equals_single_calls(engine, settings):
+    """concurrent `retrieve` calls share ONE K1 + K2 + K3 batch through CoalescedRetriever and each
+    comes back exactly as its own RAG2Retriever.retrieve would (same contexts, bit-identical rrf / rerank scores,
+    refusal and max score); the tool response carries the reference's keys (crm_knowledge.py:126-182)."""
+    from triple_hybrid_rag_b200.tool import CoalescedRetriever, format_tool_response, search_knowledge_base_rag2
+    n, D, Td = 1200, 64, 64
+    chunks, emb, parents = _corpus(n, D, seed=21)
+    g = torch.Generator().manual_seed(2)
+    tok = torch.randn((n, Td, 128), generator=g)
+    tok = (tok / tok.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+    ix = ResidentIndex(engine, chunks, emb, parents, blk_docs=512, token_store=tok)
+    queries = [f"w{3 * i % 50} w{7 * i % 120} w{i % 9}" for i in range(10)]
+    table = {q: (emb[11 * i] + 0.4 * torch.randn(D, generator=g)).tolist() for i, q in enumerate(queries)}
+    qtoks = {q: torch.randn((16, 128), generator=g) for q in queries}
+    r = GpuRAG2Retriever(org_id="t", embedder=_Embedder(table), index=ix, token_encoder=lambda q: qtoks[q],
+                         lexical_match="any")
+    settings.rag2_rerank_top_k, settings.rag2_safety_threshold, settings.rag2_denoise_alpha = 20, 0.5, 0.95
+    colls = [None, "a", "b", None, "a", None, None, "b", None, None]
+    direct = [asyncio.run(r.retrieve(q, collection=c, top_k=5, skip_planning=True)) for q, c in zip(queries, colls)]
+
+    async def go():
+        cr = CoalescedRetriever(r, max_batch=16, max_wait_ms=30)
+        out = await asyncio.gather(*[cr.retrieve(q, collection=c, top_k=5, skip_planning=True) for q, c in zip(queries, colls)])
+        await cr.drain()
+        cr.close()
+        return cr, out
+    cr, out = asyncio.run(go())
+    assert cr._fe.batches == [10]                     # one launch served all ten calls
+    key = lambda res: (res.refused, res.refusal_reason, float(res.max_rerank_score).hex(),
+                       [(c.child_id, c.rrf_score.hex(), float(c.rerank_score).hex(), c.lexical_rank, c.semantic_rank, c.parent_text)
+                        for c in res.contexts])
+    assert [key(x) for x in out] == [key(x) for x in direct]
+    assert any(not x.refused and x.contexts for x in out)
+    d = format_tool_response(queries[0], colls[0], out[0])
+    assert d["search_type"] == "rag2_triple_hybrid" and d["success"]
+    if not out[0].refused:
+        assert d["result_count"] == len(out[0].contexts) and set(d["results"][0]) >= {
+            "chunk_id", "parent_id", "document_id", "content", "page", "modality", "relevance_rank", "similarity_score",
+            "rerank_score", "is_table", "lexical_rank", "semantic_rank", "graph_rank"}
+        assert d["results"][0]["content"].startswith("parent text") and {"planning", "retrieval"} <= set(d["timings_ms"])
+    d2 = search_knowledge_base_rag2(queries[1], colls[1], 5, retriever=_SkipPlanning(r))
+    assert d2["query"] == queries[1] and d2["category"] == "a" and ("refused" in d2 or d2["result_count"] <= 5)
+
+
+class _SkipPlanning:
+    """retrieve(query=, collection=, top_k=) as the tool calls it, with the fallback plan (no LLM planner here)."""
+    def __init__(self, r):
+        self.r = r
+
+    def retrieve(self, query, collection=None, top_k=None):
+        return self.r.retrieve(query, collection=collection, top_k=top_k, skip_planning=True)

@@ -530,18 +530,20 @@ class _GpuScoring:
     def retrieve_batch(self, queries: Sequence[str], query_vectors: torch.Tensor,
                        keywords: Sequence[Sequence[str]], graph_ids: Optional[Sequence[Sequence[str]]] = None,
                        top_k: int = 100, k_sem: int = 100, k_lex: int = 50, weights: Optional[Dict[str, float]] = None,
-                       collections: Optional[Sequence[Optional[str]]] = None) -> List[List[RetrievalCandidate]]:
+                       collections: Optional[Sequence[Optional[str]]] = None,
+                       tie_mode: int = _lib.TIE_CHUNK_ID) -> List[List[RetrievalCandidate]]:
         """B queries in one pass of K1 + K2 + K3 (no planner, no rerank): returns per query the fused
-        candidates (rrf_score and channel ranks set), ties by chunk id.  query_vectors [B, D].
+        candidates (rrf_score and channel ranks set).  query_vectors [B, D].  tie_mode: exact RRF ties by chunk id
+        (north_star) or TIE_INSERTION, the reference's stable-sort order (first seen lexical -> semantic -> graph).
         collections: per query, the collection its semantic and lexical hits must belong to (None: any)."""
         from .pipeline import TripleHybridSearcher
         eng, ix = self._need_engine(), self.index
         with eng.lock:     # a batch is several C-ABI calls on one handle: one thread at a time (engine.lock)
             return self._retrieve_batch_locked(TripleHybridSearcher(eng), queries, query_vectors, keywords, graph_ids,
-                                               top_k, k_sem, k_lex, weights, collections)
+                                               top_k, k_sem, k_lex, weights, collections, tie_mode)
 
     def _retrieve_batch_locked(self, s, queries, query_vectors, keywords, graph_ids, top_k, k_sem, k_lex, weights,
-                               collections):
+                               collections, tie_mode):
         eng, ix = self.engine, self.index
         s.has_dense = s.has_bm25 = True
         B = len(queries)
@@ -567,7 +569,7 @@ class _GpuScoring:
             want = torch.tensor([-1 if c is None else ix.tag_of.get(c, 0xfffe) for c in collections], dtype=torch.int32,
                                 device=eng.device)
         out = s.search(Q, qt, qo, g, weights=wt, k_sem=min(k_sem, len(ix.rows)), k_lex=k_lex, top_k=top_k, want=want,
-                       require_all=self.lexical_match == "all")
+                       require_all=self.lexical_match == "all", tie_mode=tie_mode)
         eng.sync()
         ids, rrf, rk, cnt = out.ids.tolist(), out.rrf.tolist(), out.ranks.tolist(), out.count.tolist()
         res = []
