@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 8
+#define THR_ABI_VERSION 9
 
 enum {
   THR_OK = 0,
@@ -250,8 +250,9 @@ int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int
  *
  * thr_rerank_rows: the first C candidates of each fused list -> rows of THIS rank's token store.
  *   ids [B, stride] int64 fused ids (-1 padded), count [B]; a candidate whose id lies in [id_lo, id_hi) (the chunk-id
- *   range this rank owns) maps to row (id - id_lo), taken modulo `period` when period > 0 (a synthetic store that
- *   repeats); every other slot maps to -1, which thr_maxsim scores -inf.  rows [B, C] int64.
+ *   range this rank owns) maps to row (id - id_lo + row_off), taken modulo `period` when period > 0 (a synthetic store
+ *   that repeats: row_off = id_lo % period makes the row a function of the GLOBAL id, whatever the sharding); every other
+ *   slot maps to -1, which thr_maxsim scores -inf.  rows [B, C] int64.
  * With a sharded corpus the ranks then exchange the [B, C] float scores with one all-reduce(MAX) (exactly one rank owns
  * a candidate); single GPU: no exchange.
  *
@@ -265,7 +266,7 @@ int thr_maxsim(thr_handle* h, const void* Qtok, const int32_t* q_len, int B, int
  *   out_n [B], refused [B] uint8, max_score [B].  1 <= C <= 256.
  */
 int thr_rerank_rows(thr_handle* h, const int64_t* ids, const int32_t* count, int B, int C, int stride,
-                    int64_t id_lo, int64_t id_hi, int64_t period, int64_t* rows, void* stream);
+                    int64_t id_lo, int64_t id_hi, int64_t period, int64_t row_off, int64_t* rows, void* stream);
 int thr_rerank_finish(thr_handle* h, int B, int C, int stride, const int64_t* ids, const double* rrf,
                       const int32_t* count, const float* raw, int Tq, double threshold, double alpha, int top_k,
                       int64_t* out_ids, double* out_rerank, double* out_rrf, uint8_t* out_keep, int32_t* out_n,

@@ -34,8 +34,7 @@ outs = {}
 for mode in ("peer", "nccl"):
     s = TripleHybridSearcher(eng, group=dist.group.WORLD, exchange=mode)
     s.set_dense(X[lo:hi].to(dev), id_base=lo); s.set_bm25(loc, id_base=lo)
-    # shard boundaries are multiples of 16384 and P = 50000 is not: the local store is the rows (lo + j) % P for j < P
-    s.set_token_store(store[(torch.arange(P) + lo) % P].to(dev).contiguous(), lo, hi, period=P)
+    s.set_token_store(store.to(dev), lo, hi, period=P, row_off=lo % P)     # row = global id % P on every rank
     for it in range(5):   # several steps: both buffer halves and growing sequence numbers; a smaller batch in between
         if it == 2:
             s.search(Q[:40], *pack_queries(synth.bm25_queries(B, V=V, min_rank=50)[:40], dev), graph[:40], k_sem=k, k_lex=k, top_k=k)

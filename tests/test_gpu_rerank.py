@@ -94,3 +94,6 @@ def test_rerank_stage_sharded_rows_and_scores(engine):
     rows = engine.rerank_rows(ids.to(dev), count.to(dev), C, 100, 400, period=7).cpu()
     exp = torch.where((cand >= 100) & (cand < 400), (cand - 100) % 7, torch.full_like(cand, -1))
     assert torch.equal(rows, exp)
+    # row_off = id_lo % period: the row is a function of the global id
+    rows = engine.rerank_rows(ids.to(dev), count.to(dev), C, 100, 400, period=7, row_off=100 % 7).cpu()
+    assert torch.equal(rows, torch.where((cand >= 100) & (cand < 400), cand % 7, torch.full_like(cand, -1)))

@@ -71,7 +71,8 @@ struct Bm25Args {
   uint64_t* wlists;       // [grid][warps][kListCap] per-warp candidate lists
   unsigned* tau_q;        // [B] running threshold per query (fp32 bits of a score >= 0), shared by its units
   int require_all;        // AND semantics: a doc must contain every (distinct, known) query term
-  int pf_dist;            // L2 prefetch distance in ranges (0: none)
+  int pf_dist;            // L2 prefetch of a warp's next grab: 0 = off (needs static_grabs)
+  int static_grabs;       // 1: warp w takes grabs w, w + nw, ... of a unit; 0: grabs are handed out dynamically
   thr_dev_status* status;
 };
 
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     __syncthreads();
     const int unit = vsh->unit;
     if (unit < 0) break;
-    const int q = a.units[unit].q, r1 = a.units[unit].r1;
+    const int q = a.units[unit].q, r0 = a.units[unit].r0, r1 = a.units[unit].r1;
     const int qlo = a.q_off[q];
     const int nt = min(a.q_off[q + 1] - qlo, kMaxTerms);   // longer queries are reported by bm25_cost_kernel
     int term = -1;
@@ -294,36 +295,70 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     // kDepth chunks, so its first chunk always lands in buffer 0 of the pipeline below.
     // Stream: kDepth chunks of <= 32 postings are in flight in registers; buffer j holds bn[j] postings of one
     // piece (lane < bn[j] has one), weight bw[j]; an empty chunk (bn = 0) is a no-op for the adds.
-    constexpr int kNewRange = 1 << 16;
+    // descriptor word z: postings of the piece (bits 0-12, <= 2048); on a range's first piece also kNewRange | range << 14
+    constexpr int kNewRange = 1 << 13;
+    constexpr int kRangeShift = 14;
     const uint32_t tb_lo = term >= 0 ? (uint32_t)__ldg(row) : 0u;          // low word of the term's first posting index
     const Posting* const tp = a.post + (term >= 0 ? __ldg(row) : 0);       // the term's first posting
     uint4* const desc = (uint4*)(desc_all + (size_t)warp * kDescCap * 16);
     uint32_t desc_u = smem_u32(desc);
     asm volatile("" : "+r"(desc_u));
     const int per_range = __popc(__ballot_sync(0xffffffffu, term >= 0)) + kDepth - 1;   // most descriptors a range takes
-    int np = 0, pend_r = 0, pend_end = 0;
+    constexpr int kListRoomForEnd = kDepth;   // empty descriptors after the last piece: the loader may run this far past it
+    // Ranges are handed out statically: a grab is gsz (<= kGrab) consecutive ranges, warp w takes grabs w, w + nw,
+    // ... of the unit.  The owner of a grab is therefore known in advance and can pull exactly its postings (one
+    // contiguous piece per term) and its skip entries into L2 one list ahead: every byte is prefetched once, by the
+    // warp that will read it (a dynamic hand-out made that a guess: +25 % DRAM traffic for 4 %).
+    const int gsz = min(kGrab, max(1, (r1 - r0) / (nw * 8)));
+    int np = 0, pend_r = 0, pend_end = 0, g_next = warp;
+    uint32_t nb0 = 0, nb1 = 0;      // posting offsets that bound this lane's term in the grab AFTER the next one taken
+    bool have_nb = false;
+    auto grab_lo = [&](int g) -> int { return r0 + min(g, 1 << 24) * gsz; };
+    auto bounds = [&](int g, uint32_t& lo_o, uint32_t& hi_o) {
+      const int lo_ = grab_lo(g);
+      lo_o = hi_o = 0;
+      if (term >= 0 && lo_ < r1) {
+        lo_o = __ldg((const uint32_t*)(row + lo_)) - tb_lo;
+        hi_o = __ldg((const uint32_t*)(row + min(min(lo_ + gsz, r1), a.n_blk))) - tb_lo;
+      }
+    };
+    auto prefetch_piece = [&](uint32_t lo_o, uint32_t hi_o) {
+      if (hi_o > lo_o) {
+        const Posting* pb = (const Posting*)((uintptr_t)(tp + lo_o) & ~(uintptr_t)15);
+        const uint32_t nby = min((uint32_t)((const uint8_t*)(tp + hi_o) - (const uint8_t*)pb), 65536u);
+        prefetch_l2_bulk(pb, (nby + 15u) & ~15u);
+      }
+    };
     auto build = [&]() {
       np = 0;
-      while (np + per_range <= kDescCap) {
+      while (np + per_range + kListRoomForEnd <= kDescCap) {
         if (pend_r >= pend_end) {
-          int r = 0;
-          if (lane == 0) {
-            r = atomicAdd(&sh->next_range, kGrab);
-            const unsigned g = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
-            if (g > vsh->tau_bits) atomicMax(&sh->tau_bits, g);
+          const int g = g_next;
+          int lo_ = grab_lo(g);
+          if (!a.static_grabs) {        // dynamic hand-out: the next gsz ranges nobody has taken yet
+            if (lane == 0) lo_ = atomicAdd(&sh->next_range, gsz);
+            lo_ = __shfl_sync(0xffffffffu, lo_, 0);
           }
-          r = __shfl_sync(0xffffffffu, r, 0);
-          if (r >= r1) break;
-          pend_r = r;
-          pend_end = min(r + kGrab, r1);
-          if (term >= 0 && a.pf_dist > 0) {   // a later grab's postings of this term -> L2 (one contiguous piece)
-            const int f0 = min(r + a.pf_dist, a.n_blk), f1 = min(r + a.pf_dist + kGrab, a.n_blk);
-            const uint32_t o0 = __ldg((const uint32_t*)(row + f0)) - tb_lo, o1 = __ldg((const uint32_t*)(row + f1)) - tb_lo;
-            if (o1 > o0) {
-              const Posting* pb = (const Posting*)((uintptr_t)(tp + o0) & ~(uintptr_t)15);
-              const uint32_t nby = min((uint32_t)((const uint8_t*)(tp + o1) - (const uint8_t*)pb), 32768u);
-              prefetch_l2_bulk(pb, (nby + 15u) & ~15u);
+          if (lo_ >= r1) break;
+          pend_r = lo_;
+          pend_end = min(lo_ + gsz, r1);
+          g_next += nw;
+          if (lane == 0) {
+            const unsigned gt = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
+            if (gt > vsh->tau_bits) atomicMax(&sh->tau_bits, gt);
+          }
+          if (a.pf_dist != 0 && a.static_grabs) {
+            // taking grab g: its successor g + nw goes to L2 now (postings: one contiguous piece per term, bounded by
+            // the skip entries loaded when grab g - nw was taken; skip entries: the two sectors its list building will
+            // read), and the bounds of g + 2 nw are loaded for the next take — nothing here is waited for.
+            if (!have_nb) { bounds(g + nw, nb0, nb1); have_nb = true; }     // the unit's first take: the one stall
+            prefetch_piece(nb0, nb1);
+            const int sk = grab_lo(g + nw);
+            if (term >= 0 && sk < r1) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + sk));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + min(sk + gsz, a.n_blk)));
             }
+            bounds(g + 2 * nw, nb0, nb1);
           }
         }
         uint32_t e[kGrab + 1];   // skip entries of [pend_r, pend_r + kGrab] relative to the term's first posting
@@ -332,7 +367,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
           e[i] = term >= 0 ? __ldg((const uint32_t*)(row + min(pend_r + i, a.n_blk))) - tb_lo : 0u;
 #pragma unroll
         for (int i = 0; i < kGrab; ++i) {
-          if (pend_r < pend_end && np + per_range <= kDescCap) {
+          if (pend_r < pend_end && np + per_range + kListRoomForEnd <= kDescCap) {
             const int cnt = (int)(e[i + 1] - e[i]);
             unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
             if (kAnd && __popc(live) < need) live = 0;   // a term without postings here: no doc of the range matches
@@ -344,7 +379,8 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
                 const bool first = (live & lt_mask) == 0u;
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + (uint32_t)(np + __popc(live & lt_mask)) * 16u),
                              "r"((uint32_t)(uintptr_t)pp), "r"((uint32_t)((uintptr_t)pp >> 32)),
-                             "r"((uint32_t)cnt | (first ? (uint32_t)kNewRange : 0u)), "r"(__float_as_uint(wgt))
+                             "r"((uint32_t)cnt | (first ? ((uint32_t)kNewRange | ((uint32_t)pend_r << kRangeShift)) : 0u)),
+                             "r"(__float_as_uint(wgt))
                              : "memory");
               }
               np += __popc(live);
@@ -357,6 +393,10 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
           }
         }
       }
+      // the end of the list: kDepth empty descriptors (the loader reads at most that many past the last piece, so the
+      // stream needs no "list used up" test per chunk)
+      if (np > 0 && lane < kListRoomForEnd)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
       __syncwarp();
     };
 
@@ -372,15 +412,15 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
 #define THR_ISSUE(j)                                                                                     \
   {                                                                                                      \
     if ((j) == 0) flag0 = 0;                                                                             \
-    if (lrem <= 0 && pi < np) {                                                                          \
+    if (lrem <= 0) {                                                                                     \
       uint32_t x_, y_, z_, w_;                                                                           \
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"                                            \
                    : "=r"(x_), "=r"(y_), "=r"(z_), "=r"(w_) : "r"(desc_u + (uint32_t)pi * 16u));         \
       ++pi;                                                                                              \
       lbase = (const Posting*)(((unsigned long long)y_ << 32) | x_);                                     \
       loff = (uint32_t)lane;                                                                             \
-      lrem = (int)(z_ & 0xffffu);                                                                        \
-      if ((j) == 0) flag0 = (int)(z_ >> 16);                                                             \
+      lrem = (int)(z_ & (uint32_t)(kNewRange - 1));                                                      \
+      if ((j) == 0) flag0 = (int)(z_ >> 13);     /* != 0 on a range's first piece: flag | range << 1 */   \
       lw = __uint_as_float(w_);                                                                          \
     }                                                                                                    \
     bn[j] = lrem;                                                                                        \
@@ -394,14 +434,14 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
   }
 
     // Adds of one chunk: predicated straight-line code (an empty chunk, bn = 0, is a no-op).  ncross / cross_doc:
-    // the lane's threshold crossings.  The slot of doc d is acc[d mod kBlk] (ranges are kBlk-aligned).
+    // the lane's threshold crossings.  The slot of doc d of the range starting at doc0 is acc0 + 4 d with
+    // acc0 = &acc[0] - 4 doc0 (mod 2^32).
 #define THR_ADD(j)                                                                                       \
   {                                                                                                      \
     asm volatile(                                                                                        \
         "{\n\t.reg .pred p, c;\n\t.reg .f32 o, n, x;\n\t.reg .u32 ad;\n\t"                               \
         "setp.lt.s32 p, %2, %3;\n\t"                                                                     \
-        "and.b32 ad, %4, %9;\n\t"                                                                        \
-        "mad.lo.u32 ad, ad, 4, %5;\n\t"                                                                  \
+        "mad.lo.u32 ad, %4, 4, %5;\n\t"                                                                  \
         "@p ld.shared.f32 o, [ad];\n\t"                                                                  \
         "mul.rn.f32 x, %6, %7;\n\t"                                                                      \
         "add.rn.f32 n, o, x;\n\t"                                                                        \
@@ -411,20 +451,18 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
         "@c add.s32 %0, %0, 1;\n\t"                                                                      \
         "@c mov.u32 %1, %4;\n\t}"                                                                        \
         : "+r"(ncross), "+r"(cross_doc)                                                                  \
-        : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(acc_u), "f"(bw[j]), "f"(__uint_as_float(bi[j])), "f"(tau),         \
-          "n"(kBlk - 1)                                                                                  \
+        : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(acc0), "f"(bw[j]), "f"(__uint_as_float(bi[j])), "f"(tau)           \
         : "memory");                                                                                     \
     if (kAnd) {                                                                                          \
       asm volatile(                                                                                      \
           "{\n\t.reg .pred p;\n\t.reg .u32 h, ad;\n\t"                                                   \
           "setp.lt.s32 p, %0, %1;\n\t"                                                                   \
-          "and.b32 ad, %2, %4;\n\t"                                                                      \
-          "add.u32 ad, ad, %3;\n\t"                                                                      \
+          "add.u32 ad, %2, %3;\n\t"                                                                      \
           "@p ld.shared.u8 h, [ad];\n\t"                                                                 \
           "@p add.u32 h, h, 1;\n\t"                                                                      \
           "@p st.shared.u8 [ad], h;\n\t}"                                                                \
           :                                                                                              \
-          : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(hit_u), "n"(kBlk - 1)                                 \
+          : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(hit0)                                                 \
           : "memory");                                                                                   \
     }                                                                                                    \
   }
@@ -440,6 +478,8 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
       THR_ISSUE(0) THR_ISSUE(1) THR_ISSUE(2) THR_ISSUE(3)
     for (;;) {   // one range per iteration, its first chunk in buffer 0
       if (bn[0] <= 0) break;            // the list is used up
+      const uint32_t doc0 = (uint32_t)(flag0 >> 1) << kShift;     // flag0 = 1 | range << 1 on a range's first chunk
+      const uint32_t acc0 = acc_u - doc0 * 4u, hit0 = hit_u - doc0;
       float tau;
       asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(tau) : "r"(tau_u));
       int ncross = 0;
@@ -460,21 +500,17 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
           float v = 0.f;
           uint32_t hc = (uint32_t)need;
           if (cross_doc != 0xffffffffu) {
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(acc_u + (cross_doc & (uint32_t)(kBlk - 1)) * 4u));
-            if (kAnd) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(hc) : "r"(hit_u + (cross_doc & (uint32_t)(kBlk - 1))));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(acc0 + cross_doc * 4u));
+            if (kAnd) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(hc) : "r"(hit0 + cross_doc));
           }
           const int before = n_list;
           append(cross_doc != 0xffffffffu && v > tau && (!kAnd || hc == (uint32_t)need), v, cross_doc);
           appended = n_list - before;
         }
       } else {
-        // Slow path (a unit's warm-up; queries with fewer than k hits): test every slot of the range.  Some lane
-        // crossed (tau <= 0: every first add does), which tells where the range starts.
-        const uint32_t any_doc = __reduce_max_sync(0xffffffffu, cross_doc == 0xffffffffu ? 0u : cross_doc);
-        const bool touched = __any_sync(0xffffffffu, cross_doc != 0xffffffffu);
-        const uint32_t doc0 = any_doc & ~(uint32_t)(kBlk - 1);
+        // Slow path (a unit's warm-up; queries with fewer than k hits): test every slot of the range.
         const int before = n_list;
-        for (int j = 0; touched && j < kBlk / 128; ++j) {
+        for (int j = 0; j < kBlk / 128; ++j) {
           if (n_list > kListCap - 128 - 32) compact();
           const float tcur = __uint_as_float(vsh->tau_bits);
           uint32_t v[4];
@@ -623,8 +659,8 @@ __global__ void bm25_cost_kernel(const int32_t* q_terms, const int32_t* q_off, c
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
 // per-range overhead (range_cost postings' worth of work: skip loads, clearing the slots), so light queries are
 // split as well.
-constexpr unsigned long long kRangeCostDefault = 64;   // clearing + bookkeeping of a range, in postings
-constexpr long long kTermCostDefault = 24;             // per (term, range) on top of the term's postings
+constexpr unsigned long long kRangeCostDefault = 150;  // list building, clearing and bookkeeping of a range, in postings (~200 instructions at ~1.3 per posting)
+constexpr long long kTermCostDefault = 15;             // per (term, range) piece on top of its postings (descriptor + a partly filled chunk)
 constexpr int kUnitsPerCtaDefault = 1;   // measured at 10M / 1.25M docs, batch 256: 1 -> 1.13 / 0.22 ms, 2 -> 1.21 / 0.26, 4 -> 1.23 / 0.33
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const unsigned long long* keys, int B, int n_blk,
                                                           int num_slots, unsigned long long kRangeCost,
@@ -759,7 +795,8 @@ struct thr_bm25_state {
   int units_per_cta;
   long long range_cost, term_cost;
   int warps;    // warps per CTA of bm25_range_kernel (0: as many as shared memory holds)
-  int pf_dist;  // L2 prefetch distance in ranges (THR_BM25_PREFETCH; < 0: the default, none)
+  int pf_dist;  // THR_BM25_PREFETCH: 1 = L2 prefetch of each warp's next grab (needs static grabs; default off)
+  int static_grabs;  // THR_BM25_STATIC: 1 = static hand-out of ranges to warps (default 0: dynamic)
 };
 
 void thr_bm25_state_free(thr_handle* h) {
@@ -808,6 +845,9 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
   st->warps = e1 ? atoi(e1) : 0;
   e1 = getenv("THR_BM25_PREFETCH");
   st->pf_dist = e1 ? atoi(e1) : -1;
+  e1 = getenv("THR_BM25_STATIC");
+  st->static_grabs = e1 ? atoi(e1) : 0;
+  if (st->pf_dist > 0) st->static_grabs = 1;
   cudaError_t e = cudaMalloc((void**)&st->df, (size_t)V * sizeof(int64_t));
   if (e != cudaSuccess) { free(st); return thr_fail(h, THR_ENOMEM, "cudaMalloc(df): %s", cudaGetErrorString(e)); }
   bm25_df_kernel<<<(V + 255) / 256, 256>>>(skip, idf, n_blk, V, st->df, h->d_status);
@@ -934,10 +974,11 @@ static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* 
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.tags = want ? st->tags : nullptr; a.want = want;
   a.wlists = (uint64_t*)(ws + o_wl); a.tau_q = (unsigned*)(ws + o_tau); a.require_all = require_all;
-  // L2 prefetch of a later grab: off by default.  Measured at 10M docs (ncu dram__bytes_read): distance 0 -> 1.217 ms,
-  // 2.42 GB read; 8 -> 1.173 ms; 16 -> 1.183 ms, 2.96 GB; 50 -> 1.206 ms, 3.35 GB (2.66 GB algorithmic): the 4 %
-  // it buys are paid with 20-40 % more DRAM traffic, which the dense kernel sharing the step cannot spare.
+  // L2 prefetch of each warp's next grab (THR_BM25_PREFETCH=0 turns it off).  With the dynamic hand-out of round 2's
+  // first version a prefetch was a guess about who reads what: at 10M docs distance 0 -> 1.217 ms, 2.42 GB of DRAM
+  // reads; 16 -> 1.183 ms, 2.96 GB; 50 -> 1.206 ms, 3.35 GB (2.66 GB algorithmic).  Static grabs make it exact.
   a.pf_dist = st->pf_dist >= 0 ? st->pf_dist : 0;
+  a.static_grabs = st->static_grabs;
   a.status = h->d_status;
   tok = thr_prof_begin(h, THR_PROF_BM25, s);
   cudaError_t le;

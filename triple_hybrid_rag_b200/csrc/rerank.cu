@@ -17,14 +17,14 @@ namespace {
 constexpr int kRerankMaxC = 256;
 
 __global__ void rerank_rows_kernel(const int64_t* ids, const int32_t* count, int B, int C, int stride,
-                                   int64_t id_lo, int64_t id_hi, int64_t period, int64_t* rows) {
+                                   int64_t id_lo, int64_t id_hi, int64_t period, int64_t row_off, int64_t* rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int q = i / C, j = i % C;
   int64_t r = -1;
   if (j < count[q]) {
     const int64_t id = ids[(size_t)q * stride + j];
-    if (id >= id_lo && id < id_hi) r = period > 0 ? (id - id_lo) % period : id - id_lo;
+    if (id >= id_lo && id < id_hi) r = period > 0 ? (id - id_lo + row_off) % period : id - id_lo + row_off;
   }
   rows[i] = r;
 }
@@ -131,14 +131,14 @@ __global__ void __launch_bounds__(kRerankMaxC) rerank_finish_kernel(const Finish
 extern "C" {
 
 int thr_rerank_rows(thr_handle* h, const int64_t* ids, const int32_t* count, int B, int C, int stride,
-                    int64_t id_lo, int64_t id_hi, int64_t period, int64_t* rows, void* stream) {
+                    int64_t id_lo, int64_t id_hi, int64_t period, int64_t row_off, int64_t* rows, void* stream) {
   if (!h) return THR_EINVAL;
   cudaSetDevice(h->device);
   THR_REQUIRE(h, B >= 0 && C >= 1 && stride >= C, "thr_rerank_rows: need C >= 1 and stride >= C");
   if (B == 0) return THR_OK;
-  THR_REQUIRE(h, ids && count && rows, "thr_rerank_rows: NULL argument");
+  THR_REQUIRE(h, ids && count && rows && row_off >= 0, "thr_rerank_rows: NULL argument or negative row_off");
   const int tok = thr_prof_begin(h, THR_PROF_RERANK, (cudaStream_t)stream);
-  rerank_rows_kernel<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ids, count, B, C, stride, id_lo, id_hi, period, rows);
+  rerank_rows_kernel<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ids, count, B, C, stride, id_lo, id_hi, period, row_off, rows);
   thr_prof_end(h, tok, (cudaStream_t)stream);
   THR_CHECK_LAUNCH(h, "rerank_rows_kernel");
   return THR_OK;

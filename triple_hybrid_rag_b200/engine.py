@@ -261,14 +261,14 @@ class Engine:
         return out
 
     # -- the batched rerank stage around K4 ---------------------------------------------------
-    def rerank_rows(self, ids: torch.Tensor, count: torch.Tensor, C: int, id_lo: int, id_hi: int, period: int = 0
-                    ) -> torch.Tensor:
+    def rerank_rows(self, ids: torch.Tensor, count: torch.Tensor, C: int, id_lo: int, id_hi: int, period: int = 0,
+                    row_off: int = 0) -> torch.Tensor:
         """Fused ids [B, stride] (+ count [B]) -> rows [B, C] of this rank's token store (-1: not owned / padding)."""
         ids = self._dev(ids, torch.int64, "ids")
         count = self._dev(count, torch.int32, "count")
         B, stride = ids.shape
         rows = torch.empty((B, C), dtype=torch.int64, device=self.device)
-        self._check(self._lib.thr_rerank_rows(self._h, _ptr(ids), _ptr(count), B, C, stride, id_lo, id_hi, period,
+        self._check(self._lib.thr_rerank_rows(self._h, _ptr(ids), _ptr(count), B, C, stride, id_lo, id_hi, period, row_off,
                                               _ptr(rows), self._stream()))
         return rows
 

@@ -135,13 +135,14 @@ class TripleHybridSearcher:
         self.has_bm25 = True
 
     def set_token_store(self, store: torch.Tensor, id_lo: int, id_hi: int, period: int = 0,
-                        lens: Optional[torch.Tensor] = None):
+                        lens: Optional[torch.Tensor] = None, row_off: int = 0):
         """This rank's late-interaction token store for the rerank stage: store [rows, Td, 128] bf16 holds the token
-        embeddings of the chunks [id_lo, id_hi) this rank owns, chunk id -> row (id - id_lo), modulo `period` when
-        period > 0 (synthetic stores that repeat; period == rows then)."""
+        embeddings of the chunks [id_lo, id_hi) this rank owns, chunk id -> row (id - id_lo + row_off), modulo `period`
+        when period > 0 (synthetic stores that repeat; period == rows then, and row_off = id_lo % period makes the row a
+        function of the global id, so every sharding sees the same token embeddings for a chunk)."""
         self.tok_store = self.engine._dev(store, torch.bfloat16, "token store")
         self.tok_lens = None if lens is None else self.engine._dev(lens, torch.int32, "token lens")
-        self.tok_lo, self.tok_hi, self.tok_period = int(id_lo), int(id_hi), int(period)
+        self.tok_lo, self.tok_hi, self.tok_period, self.tok_off = int(id_lo), int(id_hi), int(period), int(row_off)
 
     def rerank(self, out: "SearchOutput", Qtok: torch.Tensor, C: int, threshold: float, alpha: float, final_top_k: int,
                q_len: Optional[torch.Tensor] = None) -> "SearchOutput":
@@ -150,7 +151,7 @@ class TripleHybridSearcher:
         ONE all-reduce(MAX) when the corpus is sharded (a candidate is scored -inf everywhere but on its owner), and
         thr_rerank_finish orders by rerank score and applies the safety threshold / denoise on every rank."""
         eng = self.engine
-        rows = eng.rerank_rows(out.ids, out.count, C, self.tok_lo, self.tok_hi, self.tok_period)
+        rows = eng.rerank_rows(out.ids, out.count, C, self.tok_lo, self.tok_hi, self.tok_period, self.tok_off)
         raw = eng.maxsim(Qtok, self.tok_store, rows, q_len=q_len, d_len=self.tok_lens)
         if self.world > 1:
             import torch.distributed as dist
