@@ -334,7 +334,9 @@ def main():
 
     # ---- queries (replicated) ----
     if rank == 0:
-        Q = synth.dense_queries(B, D, X, n_plant=max(1, min(hi - lo, N // 8)))
+        # planted queries point at rows of the first N/16 chunks: inside rank 0's shard for every N <= 8, and the same
+        # rows whatever N (round 2's first 8-GPU run planted in min(shard, N/8) rows: a different batch at N = 8)
+        Q = synth.dense_queries(B, D, X, n_plant=max(1, min(hi - lo, N // 16)))
     else:
         Q = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
     if world > 1:
