@@ -18,6 +18,7 @@ tot = {1: [], 2: [], 3: []}
 for rep in range(4):
     for t in (1, 2, 3):
         os.environ["THR_DENSE_SEED_TILES"] = str(t)
+        eng.dense_index_set(X)      # the knob is read when the index is set (no getenv on the hot path)
         eng.dense_topk(Q, 100, 28); eng.sync(); eng.prof_reset()
         for _ in range(6):
             eng.dense_topk(Q, 100, 28)

@@ -305,89 +305,97 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     asm volatile("" : "+r"(desc_u));
     const int per_range = __popc(__ballot_sync(0xffffffffu, term >= 0)) + kDepth - 1;   // most descriptors a range takes
     constexpr int kListRoomForEnd = kDepth;   // empty descriptors after the last piece: the loader may run this far past it
-    // Ranges are handed out in grabs of gsz consecutive ranges — as many as surely fit one descriptor list, so a
-    // list is exactly one grab.  The skip entries of a grab are loaded when the PREVIOUS list is built (en[], kept in
-    // registers across that list's stream), so building a list waits for no load.  Hand-out: dynamic (an atomic
-    // counter per unit) by default; static (warp w takes grabs w, w + nw, ...) with THR_BM25_STATIC=1, which also allows
-    // THR_BM25_PREFETCH=1, an exact L2 prefetch of each warp's next grab — both measured slower.
-    const int gsz = max(1, min(min(kGrab, (kDescCap - kListRoomForEnd) / per_range), max(1, (r1 - r0) / (nw * 8))));
-    int np = 0, g_next = warp, n_lo = r1;
-    uint32_t en[kGrab + 1];
-#pragma unroll
-    for (int i = 0; i <= kGrab; ++i) en[i] = 0u;
-    bool primed = false;
+    // Ranges are handed out statically: a grab is gsz (<= kGrab) consecutive ranges, warp w takes grabs w, w + nw,
+    // ... of the unit.  The owner of a grab is therefore known in advance and can pull exactly its postings (one
+    // contiguous piece per term) and its skip entries into L2 one list ahead: every byte is prefetched once, by the
+    // warp that will read it (a dynamic hand-out made that a guess: +25 % DRAM traffic for 4 %).
+    const int gsz = min(kGrab, max(1, (r1 - r0) / (nw * 8)));
+    int np = 0, pend_r = 0, pend_end = 0, g_next = warp;
+    uint32_t nb0 = 0, nb1 = 0;      // posting offsets that bound this lane's term in the grab AFTER the next one taken
+    bool have_nb = false;
     auto grab_lo = [&](int g) -> int { return r0 + min(g, 1 << 24) * gsz; };
-    // take the next grab and issue the loads of its skip entries (offsets from the term's first posting)
-    auto reserve = [&]() {
-      int lo_ = grab_lo(g_next);
-      if (!a.static_grabs) {
-        if (lane == 0) lo_ = atomicAdd(&sh->next_range, gsz);
-        lo_ = __shfl_sync(0xffffffffu, lo_, 0);
+    auto bounds = [&](int g, uint32_t& lo_o, uint32_t& hi_o) {
+      const int lo_ = grab_lo(g);
+      lo_o = hi_o = 0;
+      if (term >= 0 && lo_ < r1) {
+        lo_o = __ldg((const uint32_t*)(row + lo_)) - tb_lo;
+        hi_o = __ldg((const uint32_t*)(row + min(min(lo_ + gsz, r1), a.n_blk))) - tb_lo;
       }
-      if (a.pf_dist != 0 && a.static_grabs && term >= 0) {     // the grab after this one -> L2
-        const int f0 = grab_lo(g_next + nw);
-        if (f0 < r1) {
-          const uint32_t o0 = __ldg((const uint32_t*)(row + f0)) - tb_lo;
-          const uint32_t o1 = __ldg((const uint32_t*)(row + min(min(f0 + gsz, r1), a.n_blk))) - tb_lo;
-          if (o1 > o0) {
-            const Posting* pb = (const Posting*)((uintptr_t)(tp + o0) & ~(uintptr_t)15);
-            const uint32_t nby = min((uint32_t)((const uint8_t*)(tp + o1) - (const uint8_t*)pb), 65536u);
-            prefetch_l2_bulk(pb, (nby + 15u) & ~15u);
-          }
-        }
-      }
-      g_next += nw;
-      n_lo = min(lo_, r1);
-      if (lo_ < r1) {
-#pragma unroll
-        for (int i = 0; i <= kGrab; ++i)
-          en[i] = term >= 0 ? __ldg((const uint32_t*)(row + min(lo_ + i, a.n_blk))) - tb_lo : 0u;
+    };
+    auto prefetch_piece = [&](uint32_t lo_o, uint32_t hi_o) {
+      if (hi_o > lo_o) {
+        const Posting* pb = (const Posting*)((uintptr_t)(tp + lo_o) & ~(uintptr_t)15);
+        const uint32_t nby = min((uint32_t)((const uint8_t*)(tp + hi_o) - (const uint8_t*)pb), 65536u);
+        prefetch_l2_bulk(pb, (nby + 15u) & ~15u);
       }
     };
     auto build = [&]() {
       np = 0;
-      if (!primed) { reserve(); primed = true; }      // the unit's first list: the one build that waits for its loads
-      const int lo_ = n_lo;
-      if (lo_ >= r1) return;
-      uint32_t e[kGrab + 1];
-#pragma unroll
-      for (int i = 0; i <= kGrab; ++i) e[i] = en[i];
-      reserve();
-      if (lane == 0) {
-        const unsigned gt = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
-        if (gt > vsh->tau_bits) atomicMax(&sh->tau_bits, gt);
-      }
-#pragma unroll
-      for (int i = 0; i < kGrab; ++i) {
-        const int r = lo_ + i;
-        if (i < gsz && r < r1) {
-          const int cnt = (int)(e[i + 1] - e[i]);
-          unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
-          if (kAnd && __popc(live) < need) live = 0;   // a term without postings here: no doc of the range matches
-          if (live) {
-            const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;
-            const int tot = __reduce_add_sync(0xffffffffu, nch);
-            if (cnt > 0) {
-              const Posting* pp = tp + e[i];
-              const bool first = (live & lt_mask) == 0u;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + (uint32_t)(np + __popc(live & lt_mask)) * 16u),
-                           "r"((uint32_t)(uintptr_t)pp), "r"((uint32_t)((uintptr_t)pp >> 32)),
-                           "r"((uint32_t)cnt | (first ? ((uint32_t)kNewRange | ((uint32_t)r << kRangeShift)) : 0u)),
-                           "r"(__float_as_uint(wgt))
-                           : "memory");
+      while (np + per_range + kListRoomForEnd <= kDescCap) {
+        if (pend_r >= pend_end) {
+          const int g = g_next;
+          int lo_ = grab_lo(g);
+          if (!a.static_grabs) {        // dynamic hand-out: the next gsz ranges nobody has taken yet
+            if (lane == 0) lo_ = atomicAdd(&sh->next_range, gsz);
+            lo_ = __shfl_sync(0xffffffffu, lo_, 0);
+          }
+          if (lo_ >= r1) break;
+          pend_r = lo_;
+          pend_end = min(lo_ + gsz, r1);
+          g_next += nw;
+          if (lane == 0) {
+            const unsigned gt = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
+            if (gt > vsh->tau_bits) atomicMax(&sh->tau_bits, gt);
+          }
+          if (a.pf_dist != 0 && a.static_grabs) {
+            // taking grab g: its successor g + nw goes to L2 now (postings: one contiguous piece per term, bounded by
+            // the skip entries loaded when grab g - nw was taken; skip entries: the two sectors its list building will
+            // read), and the bounds of g + 2 nw are loaded for the next take — nothing here is waited for.
+            if (!have_nb) { bounds(g + nw, nb0, nb1); have_nb = true; }     // the unit's first take: the one stall
+            prefetch_piece(nb0, nb1);
+            const int sk = grab_lo(g + nw);
+            if (term >= 0 && sk < r1) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + sk));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + min(sk + gsz, a.n_blk)));
             }
-            np += __popc(live);
-            const int pad = (-tot) & (kDepth - 1);
-            if (lane < pad)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
-            np += pad;
+            bounds(g + 2 * nw, nb0, nb1);
+          }
+        }
+        uint32_t e[kGrab + 1];   // skip entries of [pend_r, pend_r + kGrab] relative to the term's first posting
+#pragma unroll
+        for (int i = 0; i <= kGrab; ++i)
+          e[i] = term >= 0 ? __ldg((const uint32_t*)(row + min(pend_r + i, a.n_blk))) - tb_lo : 0u;
+#pragma unroll
+        for (int i = 0; i < kGrab; ++i) {
+          if (pend_r < pend_end && np + per_range + kListRoomForEnd <= kDescCap) {
+            const int cnt = (int)(e[i + 1] - e[i]);
+            unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+            if (kAnd && __popc(live) < need) live = 0;   // a term without postings here: no doc of the range matches
+            if (live) {
+              const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;
+              const int tot = __reduce_add_sync(0xffffffffu, nch);
+              if (cnt > 0) {
+                const Posting* pp = tp + e[i];
+                const bool first = (live & lt_mask) == 0u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + (uint32_t)(np + __popc(live & lt_mask)) * 16u),
+                             "r"((uint32_t)(uintptr_t)pp), "r"((uint32_t)((uintptr_t)pp >> 32)),
+                             "r"((uint32_t)cnt | (first ? ((uint32_t)kNewRange | ((uint32_t)pend_r << kRangeShift)) : 0u)),
+                             "r"(__float_as_uint(wgt))
+                             : "memory");
+              }
+              np += __popc(live);
+              const int pad = (-tot) & (kDepth - 1);
+              if (lane < pad)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
+              np += pad;
+            }
+            ++pend_r;
           }
         }
       }
       // the end of the list: kDepth empty descriptors (the loader reads at most that many past the last piece, so the
-      // stream needs no "list used up" test per chunk).  A grab without postings (np == 0) is an empty list: the
-      // caller asks for the next one.
-      if (lane < kListRoomForEnd)
+      // stream needs no "list used up" test per chunk)
+      if (np > 0 && lane < kListRoomForEnd)
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
       __syncwarp();
     };
@@ -462,32 +470,28 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     static_assert(kDepth == 4, "the pipeline below is unrolled by hand for four buffers");
 #pragma unroll
     for (int j = 0; j < kDepth; ++j) { bd[j] = 0u; bi[j] = 0u; bn[j] = 0; bw[j] = 0.f; }
-    // One range per iteration, its first chunk in buffer 0.  A range's epilogue (candidates, clearing its slots) runs
-    // at the top of the NEXT iteration, after that range's first loads are in flight: inside a list they already
-    // are (the stream runs ahead), and when a list is used up the next one is built and primed first — the epilogue
-    // then covers the latency of the priming loads instead of following it.
-    bool have_prev = false, done = !any_term;
-    uint32_t doc0 = 0, acc0 = 0, hit0 = 0, cross_doc = 0xffffffffu;
-    float tau = 0.f;
-    int ncross = 0;
-    for (;;) {
-      if (!done && bn[0] <= 0) {          // the list is used up (or this is the unit's first range): next list
-        do {
-          build();
-        } while (np == 0 && primed && n_lo < r1);     // grabs without a posting are skipped
-        if (np == 0) {
-          done = true;                                 // the unit's ranges are used up
-        } else {
-          pi = 0;
-          THR_ISSUE(0) THR_ISSUE(1) THR_ISSUE(2) THR_ISSUE(3)
-        }
-      }
-      if (!have_prev) {
-        if (done) break;
-      } else {
-      have_prev = false;
+    for (;;) {   // one descriptor list per iteration
+      if (!any_term) break;
+      build();
+      if (np == 0) break;
+      pi = 0;
+      THR_ISSUE(0) THR_ISSUE(1) THR_ISSUE(2) THR_ISSUE(3)
+    for (;;) {   // one range per iteration, its first chunk in buffer 0
+      if (bn[0] <= 0) break;            // the list is used up
+      const uint32_t doc0 = (uint32_t)(flag0 >> 1) << kShift;     // flag0 = 1 | range << 1 on a range's first chunk
+      const uint32_t acc0 = acc_u - doc0 * 4u, hit0 = hit_u - doc0;
+      float tau;
+      asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(tau) : "r"(tau_u));
+      int ncross = 0;
+      uint32_t cross_doc = 0xffffffffu;
+      do {
+        THR_ADD(0) THR_ISSUE(0)
+        THR_ADD(1) THR_ISSUE(1)
+        THR_ADD(2) THR_ISSUE(2)
+        THR_ADD(3) THR_ISSUE(3)
+      } while (bn[0] > 0 && !flag0);   // until buffer 0 starts another range (or is empty: the list is used up)
       __syncwarp();
-      // ---- the previous range is complete: collect its candidates, clear its slots ----
+      // ---- the range is complete: collect its candidates, clear its slots ----
       const bool scan = tau <= 0.f || __any_sync(0xffffffffu, ncross > 1);
       int appended = 0;
       if (!scan) {
@@ -543,22 +547,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
         if (n_list > kListHigh) compact();
         else raise_tau();
       }
-      if (done) break;
-      }
-      // ---- this range: buffer 0 holds its first chunk ----
-      doc0 = (uint32_t)(flag0 >> 1) << kShift;     // flag0 = 1 | range << 1 on a range's first chunk
-      acc0 = acc_u - doc0 * 4u;
-      hit0 = hit_u - doc0;
-      asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(tau) : "r"(tau_u));
-      ncross = 0;
-      cross_doc = 0xffffffffu;
-      do {
-        THR_ADD(0) THR_ISSUE(0)
-        THR_ADD(1) THR_ISSUE(1)
-        THR_ADD(2) THR_ISSUE(2)
-        THR_ADD(3) THR_ISSUE(3)
-      } while (bn[0] > 0 && !flag0);   // until buffer 0 starts another range (or is empty: the list is used up)
-      have_prev = true;
+    }
     }
 #undef THR_ISSUE
 #undef THR_ADD

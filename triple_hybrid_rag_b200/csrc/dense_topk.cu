@@ -613,6 +613,9 @@ struct thr_dense_state {
   CUtensorMap map_x;
   int cta_group;  // 2 (pair) or 1; THR_DENSE_CTA_GROUP overrides for bring-up
   const uint16_t* tags;  // [N] device, nullable
+  // tuning knobs, read from the environment ONCE, when the index is set (THR_DENSE_SEED_TILES, THR_DENSE_NO_SEED)
+  int seed_tiles;  // 0: the default for the shard size
+  int no_seed;
 };
 
 void thr_dense_state_free(thr_handle* h) {
@@ -662,6 +665,11 @@ int thr_dense_index_set(thr_handle* h, const void* X, int64_t N, int D, int64_t 
   st->cta_group = 2;
   const char* env = getenv("THR_DENSE_CTA_GROUP");
   if (env && env[0] == '1') st->cta_group = 1;
+  env = getenv("THR_DENSE_SEED_TILES");
+  st->seed_tiles = env ? atoi(env) : 0;
+  if (st->seed_tiles > kSeedTiles) st->seed_tiles = kSeedTiles;
+  env = getenv("THR_DENSE_NO_SEED");
+  st->no_seed = env && env[0] == '1';
   h->dense = st;
   return THR_OK;
 }
@@ -732,17 +740,12 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
   // (instead of from -inf), which cuts the epilogue's append work and list compactions several-fold.
   // tiles per cluster in the seed pass (<= kSeedTiles: the uncompacted lists must fit): a longer prefix gives a
   // tighter threshold but costs its own scoring and a select over n_clusters * tiles * 256 scores per query
-  int seed_tiles_env = 0;   // read per call: lets one process compare settings back to back (scripts/seed_probe.py)
-  if (const char* e = getenv("THR_DENSE_SEED_TILES")) {
-    seed_tiles_env = atoi(e);
-    if (seed_tiles_env > kSeedTiles) seed_tiles_env = kSeedTiles;
-  }
+  const int seed_tiles_env = st->seed_tiles;   // THR_DENSE_SEED_TILES, read when the index was set
   // measured at D = 1536, B = 256 (score + seed, ms): 1.25M rows 0.897 / 0.854 / 0.915 for 1 / 2 / 3 tiles,
   // 2.5M rows 1.84 / 1.76 / 1.73
   const int seed_tiles = seed_tiles_env > 0 ? seed_tiles_env : (st->N >= 2000000 ? kSeedTiles : 2);
   const int64_t seed_rows = (int64_t)n_clusters * seed_tiles * kTileN;
-  const char* noseed = getenv("THR_DENSE_NO_SEED");
-  if (st->N >= 16 * seed_rows && !(noseed && noseed[0] == '1')) {
+  if (st->N >= 16 * seed_rows && !st->no_seed) {
     ScoreArgs sa = a;
     sa.N = seed_rows;
     sa.seed_mode = 1;
