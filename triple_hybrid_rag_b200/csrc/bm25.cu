@@ -71,15 +71,8 @@ struct Bm25Args {
   uint64_t* wlists;       // [grid][warps][kListCap] per-warp candidate lists
   unsigned* tau_q;        // [B] running threshold per query (fp32 bits of a score >= 0), shared by its units
   int require_all;        // AND semantics: a doc must contain every (distinct, known) query term
-  int pf_dist;            // L2 prefetch of a warp's next grab: 0 = off (needs static_grabs)
-  int static_grabs;       // 1: warp w takes grabs w, w + nw, ... of a unit; 0: grabs are handed out dynamically
   thr_dev_status* status;
 };
-
-// Pull [p, p + bytes) into L2 (16-byte granules); no destination, no completion to wait for.
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 constexpr int kListCap = 1024;       // entries of a warp's candidate list (global memory)
@@ -87,14 +80,15 @@ constexpr int kListHigh = 512;       // compaction watermark after a range in cr
 constexpr int kListRoom = 384;       // a compaction leaves at most this many entries (>= kMaxSelB)
 constexpr int kDepth = 4;            // posting chunks (32 postings each) in flight per warp
 #ifndef THR_BM25_DESC_CAP
-#define THR_BM25_DESC_CAP 40
+#define THR_BM25_DESC_CAP 64
 #endif
 #ifndef THR_BM25_GRAB
 #define THR_BM25_GRAB 4
 #endif
 constexpr int kDescCap = THR_BM25_DESC_CAP;   // piece descriptors per warp (16 B each): >= kMaxTerms + kDepth - 1
 constexpr int kGrab = THR_BM25_GRAB;          // consecutive ranges a warp takes from its unit at a time
-static_assert(kDescCap >= kMaxTerms + kDepth - 1, "a range of a 32-term query must fit the descriptor list");
+static_assert(kDescCap >= kMaxTerms + kDepth - 1 && (kDescCap & (kDescCap - 1)) == 0,
+              "the descriptor ring holds at least a range of a 32-term query and is a power of two");
 constexpr int kHistBins = 256;
 constexpr int kHistShift = 19;                 // 16 bins per octave
 constexpr uint32_t kHistBase = 121u << 4;      // bin 0 starts at 2^-6 (everything smaller lands there too)
@@ -288,119 +282,83 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     };
 
     // ---- the unit's posting stream ------------------------------------------------------------------------
-    // Two levels.  build(): lane t <-> query term t turns the next few ranges of the unit into a list of piece
-    // descriptors in shared memory — one per (range, term with postings there), in range then query order:
-    // {pointer to the piece's first posting, postings | kNewRange on a range's first piece, idf} — all terms of a
-    // range at once (ballot + popc give the slots).  A range is padded with empty descriptors to a multiple of
-    // kDepth chunks, so its first chunk always lands in buffer 0 of the pipeline below.
+    // Two levels.  refill(): lane t <-> query term t turns the next grab of ranges into piece descriptors in a per-warp
+    // RING in shared memory — one per (range, term with postings there), in range then query order:
+    // {pointer to the piece's first posting, postings | first-of-range flag + range, idf} — all terms of a range at
+    // once (ballot + popc give the slots).  A range is padded with empty descriptors to a multiple of kDepth chunks,
+    // so its first chunk always lands in buffer 0 of the pipeline below.  The ring is refilled at range boundaries
+    // whenever a whole grab fits, so the loader normally never runs out of descriptors and the register pipeline
+    // does not drain between grabs (round 2's first descriptor version rebuilt a LIST when the previous one was used
+    // up: 34 % of the samples sat on the first add after every rebuild).
     // Stream: kDepth chunks of <= 32 postings are in flight in registers; buffer j holds bn[j] postings of one
-    // piece (lane < bn[j] has one), weight bw[j]; an empty chunk (bn = 0) is a no-op for the adds.
+    // piece (lane < bn[j] has one), weight bw[j]; an empty chunk (bn <= 0) is a no-op for the adds.
     // descriptor word z: postings of the piece (bits 0-12, <= 2048); on a range's first piece also kNewRange | range << 14
     constexpr int kNewRange = 1 << 13;
     constexpr int kRangeShift = 14;
     const uint32_t tb_lo = term >= 0 ? (uint32_t)__ldg(row) : 0u;          // low word of the term's first posting index
     const Posting* const tp = a.post + (term >= 0 ? __ldg(row) : 0);       // the term's first posting
-    uint4* const desc = (uint4*)(desc_all + (size_t)warp * kDescCap * 16);
-    uint32_t desc_u = smem_u32(desc);
+    uint32_t desc_u = smem_u32(desc_all + (size_t)warp * kDescCap * 16);
     asm volatile("" : "+r"(desc_u));
     const int per_range = __popc(__ballot_sync(0xffffffffu, term >= 0)) + kDepth - 1;   // most descriptors a range takes
-    constexpr int kListRoomForEnd = kDepth;   // empty descriptors after the last piece: the loader may run this far past it
-    // Ranges are handed out statically: a grab is gsz (<= kGrab) consecutive ranges, warp w takes grabs w, w + nw,
-    // ... of the unit.  The owner of a grab is therefore known in advance and can pull exactly its postings (one
-    // contiguous piece per term) and its skip entries into L2 one list ahead: every byte is prefetched once, by the
-    // warp that will read it (a dynamic hand-out made that a guess: +25 % DRAM traffic for 4 %).
-    const int gsz = min(kGrab, max(1, (r1 - r0) / (nw * 8)));
-    int np = 0, pend_r = 0, pend_end = 0, g_next = warp;
-    uint32_t nb0 = 0, nb1 = 0;      // posting offsets that bound this lane's term in the grab AFTER the next one taken
-    bool have_nb = false;
-    auto grab_lo = [&](int g) -> int { return r0 + min(g, 1 << 24) * gsz; };
-    auto bounds = [&](int g, uint32_t& lo_o, uint32_t& hi_o) {
-      const int lo_ = grab_lo(g);
-      lo_o = hi_o = 0;
-      if (term >= 0 && lo_ < r1) {
-        lo_o = __ldg((const uint32_t*)(row + lo_)) - tb_lo;
-        hi_o = __ldg((const uint32_t*)(row + min(min(lo_ + gsz, r1), a.n_blk))) - tb_lo;
+    // a grab: gsz consecutive ranges, handed out by the unit's atomic counter; a grab always fits half the ring
+    const int gsz = max(1, min(min(kGrab, (kDescCap / 2) / per_range), max(1, (r1 - r0) / (nw * 8))));
+    const int grab_max = gsz * per_range;
+    int np = 0, pi = 0;              // descriptors appended / fetched so far (ring positions are these modulo kDescCap)
+    auto reserve = [&]() -> int {    // the next grab's first range (>= r1: the unit's ranges are used up)
+      int lo_ = 0;
+      if (lane == 0) lo_ = atomicAdd(&sh->next_range, gsz);
+      lo_ = __shfl_sync(0xffffffffu, lo_, 0);
+      if (term >= 0 && lo_ < r1) {   // its skip entries -> L2 (two sectors hold a term's gsz + 1 entries)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lo_));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + min(lo_ + gsz, a.n_blk)));
       }
+      return lo_;
     };
-    auto prefetch_piece = [&](uint32_t lo_o, uint32_t hi_o) {
-      if (hi_o > lo_o) {
-        const Posting* pb = (const Posting*)((uintptr_t)(tp + lo_o) & ~(uintptr_t)15);
-        const uint32_t nby = min((uint32_t)((const uint8_t*)(tp + hi_o) - (const uint8_t*)pb), 65536u);
-        prefetch_l2_bulk(pb, (nby + 15u) & ~15u);
+    int next_lo = any_term ? reserve() : r1;
+    auto refill = [&]() {            // descriptors of the grab at next_lo -> ring; reserves the grab after it
+      const int lo_ = next_lo;
+      uint32_t e[kGrab + 1];         // skip entries of [lo_, lo_ + kGrab] relative to the term's first posting
+#pragma unroll
+      for (int i = 0; i <= kGrab; ++i)
+        e[i] = term >= 0 ? __ldg((const uint32_t*)(row + min(lo_ + i, a.n_blk))) - tb_lo : 0u;
+      next_lo = reserve();
+      if (lane == 0) {
+        const unsigned gt = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
+        if (gt > vsh->tau_bits) atomicMax(&sh->tau_bits, gt);
       }
-    };
-    auto build = [&]() {
-      np = 0;
-      while (np + per_range + kListRoomForEnd <= kDescCap) {
-        if (pend_r >= pend_end) {
-          const int g = g_next;
-          int lo_ = grab_lo(g);
-          if (!a.static_grabs) {        // dynamic hand-out: the next gsz ranges nobody has taken yet
-            if (lane == 0) lo_ = atomicAdd(&sh->next_range, gsz);
-            lo_ = __shfl_sync(0xffffffffu, lo_, 0);
-          }
-          if (lo_ >= r1) break;
-          pend_r = lo_;
-          pend_end = min(lo_ + gsz, r1);
-          g_next += nw;
-          if (lane == 0) {
-            const unsigned gt = *(volatile unsigned*)&a.tau_q[q];   // what the query's other units have learnt
-            if (gt > vsh->tau_bits) atomicMax(&sh->tau_bits, gt);
-          }
-          if (a.pf_dist != 0 && a.static_grabs) {
-            // taking grab g: its successor g + nw goes to L2 now (postings: one contiguous piece per term, bounded by
-            // the skip entries loaded when grab g - nw was taken; skip entries: the two sectors its list building will
-            // read), and the bounds of g + 2 nw are loaded for the next take — nothing here is waited for.
-            if (!have_nb) { bounds(g + nw, nb0, nb1); have_nb = true; }     // the unit's first take: the one stall
-            prefetch_piece(nb0, nb1);
-            const int sk = grab_lo(g + nw);
-            if (term >= 0 && sk < r1) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + sk));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + min(sk + gsz, a.n_blk)));
-            }
-            bounds(g + 2 * nw, nb0, nb1);
-          }
-        }
-        uint32_t e[kGrab + 1];   // skip entries of [pend_r, pend_r + kGrab] relative to the term's first posting
 #pragma unroll
-        for (int i = 0; i <= kGrab; ++i)
-          e[i] = term >= 0 ? __ldg((const uint32_t*)(row + min(pend_r + i, a.n_blk))) - tb_lo : 0u;
-#pragma unroll
-        for (int i = 0; i < kGrab; ++i) {
-          if (pend_r < pend_end && np + per_range + kListRoomForEnd <= kDescCap) {
-            const int cnt = (int)(e[i + 1] - e[i]);
-            unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
-            if (kAnd && __popc(live) < need) live = 0;   // a term without postings here: no doc of the range matches
-            if (live) {
-              const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;
-              const int tot = __reduce_add_sync(0xffffffffu, nch);
-              if (cnt > 0) {
-                const Posting* pp = tp + e[i];
-                const bool first = (live & lt_mask) == 0u;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(desc_u + (uint32_t)(np + __popc(live & lt_mask)) * 16u),
-                             "r"((uint32_t)(uintptr_t)pp), "r"((uint32_t)((uintptr_t)pp >> 32)),
-                             "r"((uint32_t)cnt | (first ? ((uint32_t)kNewRange | ((uint32_t)pend_r << kRangeShift)) : 0u)),
-                             "r"(__float_as_uint(wgt))
-                             : "memory");
-              }
-              np += __popc(live);
-              const int pad = (-tot) & (kDepth - 1);
-              if (lane < pad)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
-              np += pad;
+      for (int i = 0; i < kGrab; ++i) {
+        const int r = lo_ + i;
+        if (i < gsz && r < r1) {
+          const int cnt = (int)(e[i + 1] - e[i]);
+          unsigned live = __ballot_sync(0xffffffffu, cnt > 0);
+          if (kAnd && __popc(live) < need) live = 0;   // a term without postings here: no doc of the range matches
+          if (live) {
+            const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;
+            const int tot = __reduce_add_sync(0xffffffffu, nch);
+            if (cnt > 0) {
+              const Posting* pp = tp + e[i];
+              const bool first = (live & lt_mask) == 0u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(desc_u + (uint32_t)((np + __popc(live & lt_mask)) & (kDescCap - 1)) * 16u),
+                           "r"((uint32_t)(uintptr_t)pp), "r"((uint32_t)((uintptr_t)pp >> 32)),
+                           "r"((uint32_t)cnt | (first ? ((uint32_t)kNewRange | ((uint32_t)r << kRangeShift)) : 0u)),
+                           "r"(__float_as_uint(wgt))
+                           : "memory");
             }
-            ++pend_r;
+            np += __popc(live);
+            const int pad = (-tot) & (kDepth - 1);
+            if (lane < pad)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)((np + lane) & (kDescCap - 1)) * 16u), "r"(0u)
+                           : "memory");
+            np += pad;
           }
         }
       }
-      // the end of the list: kDepth empty descriptors (the loader reads at most that many past the last piece, so the
-      // stream needs no "list used up" test per chunk)
-      if (np > 0 && lane < kListRoomForEnd)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(desc_u + (uint32_t)(np + lane) * 16u), "r"(0u) : "memory");
       __syncwarp();
     };
 
-    int pi = 0, lrem = 0, flag0 = 0;
+    int lrem = 0, flag0 = 0;
     const Posting* lbase = a.post;   // the piece being streamed, the lane's next posting in it, postings left (<= 0: none)
     uint32_t loff = 0;
     float lw = 0.f;
@@ -412,10 +370,11 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
 #define THR_ISSUE(j)                                                                                     \
   {                                                                                                      \
     if ((j) == 0) flag0 = 0;                                                                             \
-    if (lrem <= 0) {                                                                                     \
+    if (lrem <= 0 && pi < np) {                                                                          \
       uint32_t x_, y_, z_, w_;                                                                           \
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"                                            \
-                   : "=r"(x_), "=r"(y_), "=r"(z_), "=r"(w_) : "r"(desc_u + (uint32_t)pi * 16u));         \
+                   : "=r"(x_), "=r"(y_), "=r"(z_), "=r"(w_)                                              \
+                   : "r"(desc_u + (uint32_t)(pi & (kDescCap - 1)) * 16u));                               \
       ++pi;                                                                                              \
       lbase = (const Posting*)(((unsigned long long)y_ << 32) | x_);                                     \
       loff = (uint32_t)lane;                                                                             \
@@ -470,14 +429,13 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     static_assert(kDepth == 4, "the pipeline below is unrolled by hand for four buffers");
 #pragma unroll
     for (int j = 0; j < kDepth; ++j) { bd[j] = 0u; bi[j] = 0u; bn[j] = 0; bw[j] = 0.f; }
-    for (;;) {   // one descriptor list per iteration
-      if (!any_term) break;
-      build();
-      if (np == 0) break;
-      pi = 0;
-      THR_ISSUE(0) THR_ISSUE(1) THR_ISSUE(2) THR_ISSUE(3)
     for (;;) {   // one range per iteration, its first chunk in buffer 0
-      if (bn[0] <= 0) break;            // the list is used up
+      // keep the ring ahead of the loader: append grabs while a whole one fits (usually none or one per iteration)
+      while (next_lo < r1 && (np - pi) + grab_max <= kDescCap) refill();
+      if (bn[0] <= 0) {                 // the pipeline is empty: the unit's start, or its ranges are used up
+        if (pi >= np) break;
+        THR_ISSUE(0) THR_ISSUE(1) THR_ISSUE(2) THR_ISSUE(3)
+      }
       const uint32_t doc0 = (uint32_t)(flag0 >> 1) << kShift;     // flag0 = 1 | range << 1 on a range's first chunk
       const uint32_t acc0 = acc_u - doc0 * 4u, hit0 = hit_u - doc0;
       float tau;
@@ -489,7 +447,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
         THR_ADD(1) THR_ISSUE(1)
         THR_ADD(2) THR_ISSUE(2)
         THR_ADD(3) THR_ISSUE(3)
-      } while (bn[0] > 0 && !flag0);   // until buffer 0 starts another range (or is empty: the list is used up)
+      } while (bn[0] > 0 && !flag0);   // until buffer 0 starts another range (or is empty: no descriptor was left)
       __syncwarp();
       // ---- the range is complete: collect its candidates, clear its slots ----
       const bool scan = tau <= 0.f || __any_sync(0xffffffffu, ncross > 1);
@@ -547,7 +505,6 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
         if (n_list > kListHigh) compact();
         else raise_tau();
       }
-    }
     }
 #undef THR_ISSUE
 #undef THR_ADD
@@ -791,8 +748,6 @@ struct thr_bm25_state {
   int units_per_cta;
   long long range_cost, term_cost;
   int warps;    // warps per CTA of bm25_range_kernel (0: as many as shared memory holds)
-  int pf_dist;  // THR_BM25_PREFETCH: 1 = L2 prefetch of each warp's next grab (needs static grabs; default off)
-  int static_grabs;  // THR_BM25_STATIC: 1 = static hand-out of ranges to warps (default 0: dynamic)
 };
 
 void thr_bm25_state_free(thr_handle* h) {
@@ -839,11 +794,6 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
   st->range_cost = e1 ? atoll(e1) : (long long)kRangeCostDefault;
   e1 = getenv("THR_BM25_WARPS");
   st->warps = e1 ? atoi(e1) : 0;
-  e1 = getenv("THR_BM25_PREFETCH");
-  st->pf_dist = e1 ? atoi(e1) : -1;
-  e1 = getenv("THR_BM25_STATIC");
-  st->static_grabs = e1 ? atoi(e1) : 0;
-  if (st->pf_dist > 0) st->static_grabs = 1;
   cudaError_t e = cudaMalloc((void**)&st->df, (size_t)V * sizeof(int64_t));
   if (e != cudaSuccess) { free(st); return thr_fail(h, THR_ENOMEM, "cudaMalloc(df): %s", cudaGetErrorString(e)); }
   bm25_df_kernel<<<(V + 255) / 256, 256>>>(skip, idf, n_blk, V, st->df, h->d_status);
@@ -922,7 +872,7 @@ static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* 
   const int grid = h->num_sms;
   // warps per CTA: one accumulator (blk_docs fp32 slots) each, as many as shared memory holds (at most 32)
   const size_t fixed = (size_t)kListCap * 8 + sizeof(RangeShared) + 256;
-  const size_t per_warp = (size_t)st->blk_docs * (require_all ? 5 : 4) + kDescCap * 16;   // fp32 slots (+ u8 hit counts) + piece list
+  const size_t per_warp = (size_t)st->blk_docs * (require_all ? 5 : 4) + kDescCap * 16;   // fp32 slots (+ u8 hit counts) + descriptor ring
   int warps = (int)((232448 - fixed) / per_warp);
   if (warps > 32) warps = 32;
   if (st->warps > 0 && st->warps < warps) warps = st->warps;
@@ -966,11 +916,6 @@ static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* 
   a.work_counter = counter; a.B = B; a.k = k; a.part_keys = part_keys; a.part_cnt = part_cnt;
   a.tags = want ? st->tags : nullptr; a.want = want;
   a.wlists = (uint64_t*)(ws + o_wl); a.tau_q = (unsigned*)(ws + o_tau); a.require_all = require_all;
-  // L2 prefetch of each warp's next grab (THR_BM25_PREFETCH=0 turns it off).  With the dynamic hand-out of round 2's
-  // first version a prefetch was a guess about who reads what: at 10M docs distance 0 -> 1.217 ms, 2.42 GB of DRAM
-  // reads; 16 -> 1.183 ms, 2.96 GB; 50 -> 1.206 ms, 3.35 GB (2.66 GB algorithmic).  Static grabs make it exact.
-  a.pf_dist = st->pf_dist >= 0 ? st->pf_dist : 0;
-  a.static_grabs = st->static_grabs;
   a.status = h->d_status;
   tok = thr_prof_begin(h, THR_PROF_BM25, s);
   cudaError_t le;
