@@ -139,7 +139,9 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
  *   postings inside range r (so skip[t*n_blk] .. skip[(t+1)*n_blk] is term t's whole list: the
  *   usual CSR indptr is skip[::n_blk]);  idf [V] float.
  * blk_docs must be a power of two in [256, 2048] (the skip granularity: one warp of the kernel owns one range at a
- * time).  idf must be >= 0 (BM25's ln(1 + ...) always is): the kernel relies on partial sums never decreasing.
+ * time).  idf must be >= 0 (BM25's ln(1 + ...) always is: the kernel relies on partial sums never decreasing) and,
+ * unless 0, lie in [2^-40, 2^20]; impacts must be BM25's (0 <= impact < k1 + 1; anything below 2^15 is safe): the
+ * kernel accumulates sums scaled by 2^-40 (exactly: a power of two) to keep two bits of every slot for a generation tag.
  * Arrays stay resident (not copied).
  */
 int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,

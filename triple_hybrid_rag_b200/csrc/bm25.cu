@@ -89,6 +89,17 @@ constexpr int kDescCap = THR_BM25_DESC_CAP;   // piece descriptors per warp (16 
 constexpr int kGrab = THR_BM25_GRAB;          // consecutive ranges a warp takes from its unit at a time
 static_assert(kDescCap >= kMaxTerms + kDepth - 1 && (kDescCap & (kDescCap - 1)) == 0,
               "the descriptor ring holds at least a range of a 32-term query and is a power of two");
+// Generation tags: a slot holds {2-bit generation tag, 30-bit fp32 pattern of the SCALED partial sum}.  All scores of
+// a range are accumulated multiplied by 2^-40 (idf is scaled once per unit; a power-of-two factor commutes with every
+// fp32 rounding as long as nothing under- or overflows, so the final score times 2^40 is bit-identical to the unscaled
+// sum): scaled sums stay below 2.0, so bits 31 and 30 of their patterns are free.  A range stamps the slots it writes
+// with its generation (range count of this warp modulo 4); a slot whose tag is another generation reads as 0, so the
+// 8 KB of a warp's accumulator are cleared once per FOUR ranges instead of after every range — clearing was 64 of the
+// ~155 shared-memory wavefronts per range, on the pipe that limits this kernel.
+// Requirements (checked when the index is set): idf == 0 or 2^-40 <= idf <= 2^20; impacts are BM25's (< k1 + 1).
+constexpr float kAccScale = 9.094947017729282e-13f;   // 2^-40
+constexpr float kAccUnscale = 1099511627776.f;         // 2^40
+constexpr uint32_t kAccMask = 0x3fffffffu;
 constexpr int kHistBins = 256;
 constexpr int kHistShift = 19;                 // 16 bins per octave
 constexpr uint32_t kHistBase = 121u << 4;      // bin 0 starts at 2^-6 (everything smaller lands there too)
@@ -176,12 +187,12 @@ __device__ int list_select(uint64_t* list, int n, int k, uint64_t* scratch, int*
 // kAnd: AND semantics (thr_bm25_topk_ex with THR_BM25_REQUIRE_ALL) — a second per-doc array counts the terms that
 // hit the doc; only docs hit by every distinct known term of the query are candidates.
 template <int kBlk, bool kAnd>
-__global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kernel(const Bm25Args a) {
+__global__ void __launch_bounds__(kBlk == 2048 ? 768 : 1024, 1) bm25_range_kernel(const Bm25Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sm0 = smem_raw + (base - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  float* acc_all = (float*)gen;                                        // [nw][kBlk]
+  float* acc_all = (float*)sm0;                                        // [nw][kBlk]
   uint8_t* hit_all = (uint8_t*)(acc_all + (size_t)nw * kBlk);          // [nw][kBlk] matched-term counts (kAnd)
   uint64_t* scratch = (uint64_t*)(hit_all + (kAnd ? (size_t)nw * kBlk : 0));   // [kListCap]
   uint8_t* desc_all = (uint8_t*)(scratch + kListCap);                  // [nw][kDescCap] 16-byte piece descriptors
@@ -200,6 +211,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
   uint32_t tau_u = smem_u32(&sh->tau_bits);
   asm volatile("" : "+r"(acc_u), "+r"(hit_u), "+r"(tau_u));
   uint64_t* const list = a.wlists + ((size_t)blockIdx.x * nw + warp) * kListCap;
+  uint32_t gen = 0;     // generation of the range this warp works on (all slots are 0 = generation 0, value 0 at start)
   const unsigned lt_mask = (1u << lane) - 1u;
   constexpr int kShift = kBlk == 2048 ? 11 : kBlk == 1024 ? 10 : kBlk == 512 ? 9 : 8;
   static_assert((1 << kShift) == kBlk, "kBlk must be 256, 512, 1024 or 2048");
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
     float wgt = 0.f;
     if (lane < nt) {
       term = a.q_terms[qlo + lane];
-      if (term < 0 || term >= a.V) term = -1; else wgt = a.idf[term];
+      if (term < 0 || term >= a.V) term = -1; else wgt = a.idf[term] * kAccScale;   // exact: a power of two
     }
     int need = 0;      // AND semantics: distinct known terms of the query; an unknown term -> no doc can match
     bool and_dead = false;
@@ -398,19 +410,28 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
 #define THR_ADD(j)                                                                                       \
   {                                                                                                      \
     asm volatile(                                                                                        \
-        "{\n\t.reg .pred p, c;\n\t.reg .f32 o, n, x;\n\t.reg .u32 ad;\n\t"                               \
+        "{\n\t.reg .pred p, c, g;\n\t.reg .f32 o, n, x;\n\t.reg .u32 ad, v, t;\n\t"                      \
         "setp.lt.s32 p, %2, %3;\n\t"                                                                     \
         "mad.lo.u32 ad, %4, 4, %5;\n\t"                                                                  \
-        "@p ld.shared.f32 o, [ad];\n\t"                                                                  \
+        "mov.u32 v, 0;\n\t"                                                                              \
+        "@p ld.shared.u32 v, [ad];\n\t"                                                                  \
+        "and.b32 t, v, 0xc0000000;\n\t"            /* the slot's generation tag */                       \
+        "setp.eq.u32 g, t, %9;\n\t"                                                                      \
+        "and.b32 v, v, 0x3fffffff;\n\t"                                                                  \
+        "selp.u32 v, v, 0, g;\n\t"                 /* another generation's value reads as 0 */           \
+        "mov.b32 o, v;\n\t"                                                                              \
         "mul.rn.f32 x, %6, %7;\n\t"                                                                      \
         "add.rn.f32 n, o, x;\n\t"                                                                        \
-        "@p st.shared.f32 [ad], n;\n\t"                                                                  \
+        "mov.b32 v, n;\n\t"                                                                              \
+        "or.b32 v, v, %9;\n\t"                                                                           \
+        "@p st.shared.u32 [ad], v;\n\t"                                                                  \
         "setp.gt.and.f32 c, n, %8, p;\n\t"                                                               \
         "setp.le.and.f32 c, o, %8, c;\n\t"                                                               \
         "@c add.s32 %0, %0, 1;\n\t"                                                                      \
         "@c mov.u32 %1, %4;\n\t}"                                                                        \
         : "+r"(ncross), "+r"(cross_doc)                                                                  \
-        : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(acc0), "f"(bw[j]), "f"(__uint_as_float(bi[j])), "f"(tau)           \
+        : "r"(lane), "r"(bn[j]), "r"(bd[j]), "r"(acc0), "f"(bw[j]), "f"(__uint_as_float(bi[j])), "f"(tau_s),        \
+          "r"(gtag)                                                                                      \
         : "memory");                                                                                     \
     if (kAnd) {                                                                                          \
       asm volatile(                                                                                      \
@@ -440,6 +461,8 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
       const uint32_t acc0 = acc_u - doc0 * 4u, hit0 = hit_u - doc0;
       float tau;
       asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(tau) : "r"(tau_u));
+      const float tau_s = tau * kAccScale;                         // the threshold in the accumulator's scale (exact)
+      const uint32_t gtag = gen << 30;                             // this range's generation tag
       int ncross = 0;
       uint32_t cross_doc = 0xffffffffu;
       do {
@@ -458,7 +481,9 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
           float v = 0.f;
           uint32_t hc = (uint32_t)need;
           if (cross_doc != 0xffffffffu) {
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(acc0 + cross_doc * 4u));
+            uint32_t vb;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vb) : "r"(acc0 + cross_doc * 4u));
+            v = __uint_as_float(vb & kAccMask) * kAccUnscale;      // written in this range: the tag is gtag
             if (kAnd) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(hc) : "r"(hit0 + cross_doc));
           }
           const int before = n_list;
@@ -475,13 +500,15 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                        : "r"(acc_u + (uint32_t)(j * 32 + lane) * 16u));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = (v[c] & ~kAccMask) == gtag ? (v[c] & kAccMask) : 0u;
           const uint32_t m = max(max(v[0], v[1]), max(v[2], v[3]));
           uint32_t hc4 = 0u;
           if (kAnd) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hc4) : "r"(hit_u + (uint32_t)(j * 32 + lane) * 4u));
           if (__any_sync(0xffffffffu, m != 0u)) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float x = __uint_as_float(v[c]);
+              const float x = __uint_as_float(v[c]) * kAccUnscale;
               const uint32_t doc = doc0 + (uint32_t)(j * 32 + lane) * 4u + c;
               const bool all = !kAnd || ((hc4 >> (8 * c)) & 255u) == (uint32_t)need;
               append(x > tcur && x > 0.f && all, x, doc);
@@ -491,10 +518,13 @@ __global__ void __launch_bounds__(kBlk == 2048 ? 800 : 1024, 1) bm25_range_kerne
         appended = n_list - before;
       }
       __syncwarp();
+      gen = (gen + 1u) & 3u;
+      if (gen == 0u) {      // the tags wrap: clear the accumulator (once per four ranges)
 #pragma unroll
-      for (int j = 0; j < kBlk / 128; ++j)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(acc_u + (uint32_t)(j * 32 + lane) * 16u), "r"(0u)
-                     : "memory");
+        for (int j = 0; j < kBlk / 128; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(acc_u + (uint32_t)(j * 32 + lane) * 16u), "r"(0u)
+                       : "memory");
+      }
       if (kAnd) {
 #pragma unroll
         for (int j = 0; j < kBlk / 128; ++j)
@@ -590,7 +620,9 @@ __global__ void bm25_df_kernel(const int64_t* skip, const float* idf, int n_blk,
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V) return;
   df[t] = skip[(size_t)(t + 1) * n_blk] - skip[(size_t)t * n_blk];
-  if (!(idf[t] >= 0.f)) dev_report(status, THR_EINVAL, 461, t);
+  // idf >= 0 (partial sums never decrease) and, unless 0, within [2^-40, 2^20] (the accumulator's scaled range)
+  if (!(idf[t] >= 0.f) || (idf[t] > 0.f && (idf[t] < 9.094947017729282e-13f || idf[t] > 1048576.f)))
+    dev_report(status, THR_EINVAL, 461, t);
 }
 
 // Single block: cut queries into units of roughly equal cost.  A range costs its postings plus a fixed
@@ -807,7 +839,7 @@ int thr_bm25_index_set(thr_handle* h, const int64_t* skip, const void* postings,
     const long long t = h->h_status->aux;
     h->h_status->code = 0;
     cudaFree(st->df); free(st);
-    return thr_fail(h, THR_EINVAL, "thr_bm25_index_set: idf[%lld] is negative or NaN (idf must be >= 0)", t);
+    return thr_fail(h, THR_EINVAL, "thr_bm25_index_set: idf[%lld] is negative, NaN or outside {0} U [2^-40, 2^20] (idf must be >= 0)", t);
   }
   h->launches++;
   h->bm25 = st;
