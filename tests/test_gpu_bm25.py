@@ -69,6 +69,14 @@ def test_bm25_rejects_negative_idf(engine):
     bad[7] = -1.0
     with pytest.raises(ThrError, match="idf"):
         engine.bm25_index_set(d.skip, d.postings, bad, d.n_docs, d.blk_docs, d.V)
+    for v in (3.0e6, 1e-13, float("nan")):     # outside {0} U [2^-40, 2^20]: the accumulator's scaled range
+        bad = d.idf.clone()
+        bad[3] = v
+        with pytest.raises(ThrError, match="idf"):
+            engine.bm25_index_set(d.skip, d.postings, bad, d.n_docs, d.blk_docs, d.V)
+    ok = d.idf.clone()
+    ok[3] = 0.0                                # a zero weight is fine (the term contributes nothing)
+    engine.bm25_index_set(d.skip, d.postings, ok, d.n_docs, d.blk_docs, d.V)
     engine.bm25_index_set(d.skip, d.postings, d.idf, d.n_docs, d.blk_docs, d.V)
 
 
