@@ -511,7 +511,7 @@ def main():
 
     stages_all = None
     if world > 1:  # every rank's per-kernel times (the step is as slow as the slowest shard)
-        mine = {n: round(ms / max(c, 1), 4) for n, (ms, c) in prof.items()}
+        mine = {n: round(ms / args.steps, 4) for n, (ms, c) in prof.items() if c}   # per step, like stages_ms
         stages_all = [None] * world
         dist.all_gather_object(stages_all, mine, group=group)
     if rank != 0:
@@ -533,7 +533,11 @@ def main():
     flops = 2.0 * B * (hi - lo) * D
     achieved = flops / (dense_avg * 1e-3) / 1e12 if dense_avg > 0 else 0.0
     x_bytes = float(hi - lo) * D * 2
-    stages = {n: round(ms / max(c, 1), 4) for n, (ms, c) in prof.items()}
+    stages = {n: round(ms / max(c, 1), 4) for n, (ms, c) in prof.items()}       # per launch (roofline arithmetic)
+    # per STEP: a slot with two launches per step (seed = prefix scoring + select, bm25_prep = plan + merge,
+    # merge = exchange push + wait-and-merge) counts both; the values add up to the step minus launch gaps
+    stages_step = {n: round(ms / args.steps, 4) for n, (ms, c) in prof.items() if c}
+    stage_launches = {n: round(c / args.steps, 2) for n, (ms, c) in prof.items() if c}
     bm25_bytes = index.algorithmic_bytes(queries)
     bm25_ms = stages.get("bm25", 0.0)
     maxsim_ms = stages.get("maxsim", 0.0)
@@ -552,7 +556,8 @@ def main():
         "latency": {"p50_ms_batch256_e2e": statistics.median(lat) * 1e3, "p50_ms_batch1_e2e": statistics.median(lat1) * 1e3},
         "step_ms": {"p50": statistics.median(per_step), "min": min(per_step), "max": max(per_step),
                     "argmax": per_step.index(max(per_step))},
-        "stages_ms": stages,
+        "stages_ms": stages_step,
+        "stage_launches_per_step": stage_launches,
         **({"stages_ms_per_rank": stages_all} if stages_all else {}),
         "roofline": {"kernel": "dense_score_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained,
                      "unit": "TFLOP/s", "frac": achieved / sustained if sustained else None,

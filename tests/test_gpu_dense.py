@@ -67,6 +67,32 @@ def test_dense_seeded_path_large_corpus(engine):
     assert (gap > 0).all()
 
 
+@pytest.mark.parametrize("case", ["ties", "skewed_subsample"])
+def test_dense_seed_select_fallbacks(engine, case):
+    """The seed select reads the seed lists once, guided by a cut from a strided subsample (the first entries of
+    every list), and falls back to a two-level histogram when the cut is useless.  Both fallbacks, on corpora
+    large enough for the seed pass: "ties" — four distinct vectors, so tens of thousands of sample scores tie at the
+    cut (more than the kernel keeps); "skewed_subsample" — the rows the subsample sees (the head of every 512-row
+    block of the prefix) all score near 1 for query 0 while the rest of the sample does not, so fewer than K' scores
+    clear the cut.  The answer must not depend on any of this."""
+    N, D, B, k = 700_000, 64, 5, 100
+    if case == "ties":
+        base = synth.dense_block(5, 4, D)
+        X = base[torch.arange(N) % 4].contiguous()
+        Q = synth.dense_queries(B, D, X)
+        Q[0] = base[1]
+    else:
+        X = synth.dense_rows(0, N, D)
+        v = X[N - 1].clone()
+        pos = (torch.arange(0, 80_000, 512)[:, None] + torch.arange(55)[None, :]).reshape(-1)
+        scale = 0.9 + 0.1 * torch.arange(pos.numel(), dtype=torch.float32) / pos.numel()
+        X[pos] = (v.float()[None, :] * scale[:, None]).to(torch.bfloat16)
+        Q = synth.dense_queries(B, D, X)
+        Q[0] = v
+    gap = _check(engine, X, Q, k)
+    assert (gap >= 0).all()
+
+
 def test_dense_single_cta_path_agrees():
     """THR_DENSE_CTA_GROUP=1 (M=128 single-CTA MMA) must give the same answer as the CTA-pair path."""
     if not torch.cuda.is_available():

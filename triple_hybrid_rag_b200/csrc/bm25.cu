@@ -633,6 +633,7 @@ constexpr long long kTermCostDefault = 15;             // per (term, range) piec
 constexpr int kUnitsPerCtaDefault = 1;   // measured at 10M / 1.25M docs, batch 256: 1 -> 1.13 / 0.22 ms, 2 -> 1.21 / 0.26, 4 -> 1.23 / 0.33
 // One launch prepares a batch (round 2: cost, plan and order used to be three launches; at 8 GPUs the fixed
 // per-step kernels are what separates the scaling curve from linear): per-query cost -> units -> heaviest first.
+constexpr int kPlanStage = 4096;
 __global__ void __launch_bounds__(1024) bm25_plan_kernel(const int32_t* q_terms, const int32_t* q_off, const int64_t* df,
                                                           int V, long long term_cost, unsigned long long* keys,
                                                           unsigned* tau_q, thr_dev_status* status, int B, int n_blk,
@@ -642,6 +643,7 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const int32_t* q_terms,
   __shared__ unsigned long long s_tot;
   __shared__ int s_carry;
   __shared__ int s_scan[1024];
+  __shared__ unsigned s_cost[kPlanStage];
   const int tid = threadIdx.x;
   if (tid == 0) { s_tot = 0; s_carry = 0; *work_counter = 0; }
   // cost[q] = total postings of the query's terms + term_cost per (term with postings, range): the kernel's time
@@ -651,9 +653,17 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const int32_t* q_terms,
     // more terms than a warp has lanes for: reported by thr_sync, never silently truncated
     if (q_off[q + 1] - q_off[q] > kMaxTerms) dev_report(status, THR_EINVAL, 460, q);
     long long c = 0;
-    for (int i = q_off[q]; i < q_off[q + 1]; ++i) {
-      const int t = q_terms[i];
-      if (t >= 0 && t < V && df[t] > 0) c += df[t] + term_cost * n_blk;
+    const int i_end = q_off[q + 1];
+    for (int i0 = q_off[q]; i0 < i_end; i0 += 8) {   // eight terms a time: their loads do not wait for each other
+      int t[8];
+      long long d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = i0 + u < i_end ? q_terms[i0 + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) d[u] = (t[u] >= 0 && t[u] < V) ? df[t[u]] : 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (d[u] > 0) c += d[u] + term_cost * n_blk;
     }
     if (c > 0xffffffffll) c = 0xffffffffll;
     keys[q] = ((unsigned long long)c << 32) | (unsigned)(0xffffffffu - (unsigned)q);
@@ -704,11 +714,16 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const int32_t* q_terms,
   __syncthreads();
   // rank sort of the units by cost, heaviest first (a few hundred units; at most B * kMaxUnitsPerQuery)
   const int n = s_carry;
+  const bool staged = n <= kPlanStage;   // the costs of a few hundred units: compared out of shared memory
+  if (staged) {
+    for (int u = tid; u < n; u += 1024) s_cost[u] = units[u].cost;
+    __syncthreads();
+  }
   for (int u = tid; u < n; u += 1024) {
-    const unsigned cu = units[u].cost;
+    const unsigned cu = staged ? s_cost[u] : units[u].cost;
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const unsigned cj = units[j].cost;
+      const unsigned cj = staged ? s_cost[j] : units[j].cost;
       rank += (cj > cu || (cj == cu && j < u)) ? 1 : 0;
     }
     order[rank] = u;
@@ -745,7 +760,7 @@ __global__ void __launch_bounds__(256) bm25_merge_kernel(const uint64_t* part_ke
           bool swap = desc_block ? (y > x) : (x > y);
           if (swap) { keys[lo] = y; keys[hi] = x; }
         }
-        __syncthreads();
+        bitonic_stage_sync(size, stride, P, 32);
       }
     }
   }

@@ -135,6 +135,17 @@ __device__ __forceinline__ bool radix_find_digit(const uint32_t* hist, int want,
   return mine;
 }
 
+// The barrier after one compare-exchange stage (size, stride) of a shared-memory bitonic network over P slots.
+// A stage whose stride is <= `local` only moves data inside blocks of 2 * local consecutive slots, and each block
+// belongs to one warp (pair layout, thread i owns pairs i, i + blockDim, ...: local = 32; slot layout, thread i owns
+// slot i and its partner i ^ stride: local = 16).  Such a stage needs a warp barrier only; the CTA barrier is kept
+// around the strides that couple warps (before one, after one, and after the last stage).
+__device__ __forceinline__ void bitonic_stage_sync(int size, int stride, int P, int local) {
+  const int next = stride > 1 ? (stride >> 1) : size;   // the first stride of the next size is `size`
+  if (stride > local || next > local || (stride == 1 && size >= P)) __syncthreads();
+  else __syncwarp();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

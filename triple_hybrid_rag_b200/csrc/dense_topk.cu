@@ -34,7 +34,8 @@ constexpr int kTmemCols = 512;
 constexpr int kCap = 1024;         // candidate slots per (cluster, query); raw keys {~idx, score bits}
 constexpr int kMaxSel = 256;       // largest K' = k + margin
 constexpr int kScoreThreads = 192;
-constexpr int kFinalThreads = 256;
+constexpr int kFinalThreads = 512;
+constexpr int kMaxClusters = 160;    // finalize / seed select: clusters of one launch (<= SMs / cta_group), a multiple of 32
 constexpr int kSeedTiles = 3;      // tiles per cluster in the seed pass: 3 x 256 candidates fit a list without compaction
 
 template <int G> struct ScoreCfg {
@@ -129,7 +130,10 @@ __device__ uint64_t warp_compact_topk(uint64_t* row, int n, int ksel, uint32_t l
   return mn;
 }
 
-template <int G>
+// kSeed: the seed pass (a.seed_mode): thresholds stay at -inf, lists stay uncompacted, and without a tag filter every
+// score of a tile is stored — with 32-byte stores, four entries a time (the generic append path stores 8 bytes per lane
+// per instruction into 32 different rows: at one wavefront per row that path alone was ~2/3 of the seed pass).
+template <int G, bool kSeed>
 __global__ void __launch_bounds__(kScoreThreads, 1)
 dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                    const ScoreArgs a) {
@@ -291,7 +295,28 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const int64_t col0 = t * kTileN;
         const int ncols = (int)min((int64_t)kTileN, a.N - col0);
         uint64_t* wptr = rowbuf + cnt;
-        if (ncols == kTileN) {
+        if (kSeed && a.tags == nullptr && ncols == kTileN) {
+          // seed pass, full tile, no tag filter: all kTileN scores of the row, in column order
+#pragma unroll 1
+          for (int c = 0; c < kTileN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (lane_base << 16) + (uint32_t)(acc * kTileN + c * 32), r);
+            tmem_ld_wait();
+            if (row_valid) {
+              const uint32_t inv0 = ~(uint32_t)(col0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const uint64_t e0 = ((uint64_t)r[j] << 32) | (uint64_t)(inv0 - (uint32_t)j);
+                const uint64_t e1 = ((uint64_t)r[j + 1] << 32) | (uint64_t)(inv0 - (uint32_t)(j + 1));
+                const uint64_t e2 = ((uint64_t)r[j + 2] << 32) | (uint64_t)(inv0 - (uint32_t)(j + 2));
+                const uint64_t e3 = ((uint64_t)r[j + 3] << 32) | (uint64_t)(inv0 - (uint32_t)(j + 3));
+                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(wptr + j), "l"(e0), "l"(e1), "l"(e2),
+                             "l"(e3) : "memory");
+              }
+              wptr += 32;
+            }
+          }
+        } else if (ncols == kTileN) {
           // full tile
 #pragma unroll 1
           for (int c = 0; c < kTileN / 32; ++c) {
@@ -351,7 +376,7 @@ dense_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
       }
       // final compaction of this query block: every list ends with <= K' entries
-      unsigned need = __ballot_sync(0xffffffffu, row_valid && cnt > a.ksel && !a.seed_mode);
+      unsigned need = __ballot_sync(0xffffffffu, row_valid && cnt > a.ksel && !kSeed);
       while (need) {
         const int src = __ffs(need) - 1;
         need &= need - 1;
@@ -392,44 +417,68 @@ struct FinalArgs {
   float* out_gap;
 };
 
-__global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const FinalArgs a) {
+__global__ void __launch_bounds__(kFinalThreads, 2) dense_finalize_kernel(const FinalArgs a) {
   extern __shared__ uint8_t fsm[];
   // layout: keys [n_clusters*ksel] u64 | qrow [D] bf16
   uint64_t* keys = (uint64_t*)fsm;
   __nv_bfloat16* qrow = (__nv_bfloat16*)(keys + (size_t)a.n_clusters * a.ksel);
   __shared__ uint32_t hist[256];
+  __shared__ int s_n[kMaxClusters], s_off[kMaxClusters];
   __shared__ uint64_t s_prefix;
-  __shared__ int s_want, s_m, s_nsel;
+  __shared__ unsigned long long s_minkey;
+  __shared__ int s_want, s_m, s_nsel, s_done;
   __shared__ uint64_t sel_key[kMaxSel];
   __shared__ double sel_score[kMaxSel];
   __shared__ uint32_t sel_idx[kMaxSel];
 
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_m = 0; s_nsel = 0; }
+  if (tid == 0) { s_nsel = 0; s_minkey = ~0ull; }
   for (int i = tid; i < a.D; i += kFinalThreads) qrow[i] = a.Q[(size_t)q * a.D + i];
+  // 1. gather the per-cluster lists of this query: list lengths first (one load per cluster, all in flight), an
+  //    exclusive scan over the clusters by the first warp, then one flat copy whose loads do not depend on each other
+  for (int c = tid; c < kMaxClusters; c += kFinalThreads)
+    s_n[c] = c < a.n_clusters ? min(a.cnt[(size_t)c * a.Bpad + q], a.ksel) : 0;
   __syncthreads();
-
-  // 1. gather the per-cluster lists of this query
-  for (int c = warp; c < a.n_clusters; c += kFinalThreads / 32) {
-    const int n = min(a.cnt[(size_t)c * a.Bpad + q], a.ksel);
-    const uint64_t* src = a.cand + ((size_t)c * a.Bpad + q) * kCap;
-    int base = 0;
-    if (lane == 0 && n > 0) base = atomicAdd(&s_m, n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (int i = lane; i < n; i += 32) keys[base + i] = raw_to_orderable(src[i]);
+  if (warp == 0) {
+    constexpr int kPer = kMaxClusters / 32;
+    int n[kPer], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { n[i] = s_n[lane * kPer + i]; sum += n[i]; }
+    int incl = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += v;
+    }
+    int off = incl - sum;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { s_off[lane * kPer + i] = off; off += n[i]; }
+    if (lane == 31) s_m = incl;
+  }
+  __syncthreads();
+  {
+    const int total = a.n_clusters * a.ksel;
+#pragma unroll 4
+    for (int j = tid; j < total; j += kFinalThreads) {
+      const int c = j / a.ksel, i = j - c * a.ksel;
+      if (i < s_n[c]) keys[s_off[c] + i] = raw_to_orderable(a.cand[((size_t)c * a.Bpad + q) * kCap + i]);
+    }
   }
   __syncthreads();
   const int m = s_m;
   const int nsel = min(m, a.ksel);
 
-  // 2. K'-th largest key by MSD radix select (8 bits per pass); keys are distinct
+  // 2. K'-th largest key by MSD radix select (8 bits per pass); keys are distinct.  The walk stops as soon as the
+  //    bin it descends into holds exactly the keys still wanted (normally after three or four passes): every key of
+  //    that bin is selected, so the threshold is the bin's lower edge.
   uint64_t T = 0;
   if (m > a.ksel) {
-    if (tid == 0) { s_prefix = 0; s_want = a.ksel; }
+    if (tid == 0) { s_prefix = 0; s_want = a.ksel; s_done = 0; }
     for (int pass = 0; pass < 8; ++pass) {
       const int shift = 56 - 8 * pass;
-      hist[tid] = 0;
+      if (tid < 256) hist[tid] = 0;
       __syncthreads();
+      if (s_done) break;   // uniform: written before the barrier that ended the previous pass
       const uint64_t prefix = s_prefix;
       for (int i = tid; i < m; i += kFinalThreads) {
         const uint64_t key = keys[i];
@@ -443,24 +492,35 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
         if (radix_find_digit(hist, want, tid, &d, &above)) {
           s_want = want - above;
           s_prefix = prefix | ((uint64_t)d << shift);
+          if ((int)hist[d] == want - above) s_done = 1;
         }
       }
       __syncthreads();
     }
     T = s_prefix;
   }
-  // 3. collect survivors
+  // 3. collect survivors; the smallest of them is the K'-th best key (the certificate's reference score).  Their
+  //    rows are asked into L2 right away: the re-scoring below then waits on L2, not on HBM.
   for (int i = tid; i < m; i += kFinalThreads) {
     const uint64_t key = keys[i];
     if (key >= T) {
       int slot = atomicAdd(&s_nsel, 1);
       if (slot < kMaxSel) sel_key[slot] = key;
+      atomicMin(&s_minkey, (unsigned long long)key);
     }
   }
   __syncthreads();
+  {
+    const int lines = (a.D * 2 + 127) / 128;
+    for (int j = tid; j < nsel * lines; j += kFinalThreads) {
+      const int r = j / lines, l = j - r * lines;
+      const char* p = (const char*)(a.X + (size_t)key_index(sel_key[r]) * a.D) + (size_t)l * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
 
   // 4. exact re-score: fp64 dot of the bf16 inputs, one warp per survivor, fixed summation order.  Four
-  //    survivors are in flight per warp so that their (cold, scattered) row reads overlap.
+  //    survivors are in flight per warp so that their scattered row reads overlap.
   constexpr int kInFlight = 4;
   constexpr int kWarpsF = kFinalThreads / 32;
   for (int i0 = warp * kInFlight; i0 < nsel; i0 += kWarpsF * kInFlight) {
@@ -476,12 +536,14 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
 #pragma unroll
       for (int u = 0; u < kInFlight; ++u)
         xv[u] = *reinterpret_cast<const uint4*>(a.X + (size_t)idx[u] * a.D + d0);
+      double qd[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qd[e] = (double)__bfloat162float(qrow[d0 + e]);
 #pragma unroll
       for (int u = 0; u < kInFlight; ++u) {
         const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv[u]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          acc[u] = fma((double)__bfloat162float(xe[e]), (double)__bfloat162float(qrow[d0 + e]), acc[u]);
+        for (int e = 0; e < 8; ++e) acc[u] = fma((double)__bfloat162float(xe[e]), qd[e], acc[u]);
       }
     }
 #pragma unroll
@@ -492,112 +554,215 @@ __global__ void __launch_bounds__(kFinalThreads) dense_finalize_kernel(const Fin
       if (lane == 0 && i0 + u < nsel) { sel_score[i0 + u] = s; sel_idx[i0 + u] = idx[u]; }
     }
   }
-  for (int i = nsel + tid; i < kMaxSel; i += kFinalThreads) { sel_score[i] = -CUDART_INF; sel_idx[i] = 0xffffffffu; }
   __syncthreads();
 
-  // 5. bitonic sort of 256 slots by (score desc, idx asc); one slot per thread
-  for (int size = 2; size <= kMaxSel; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (tid < kMaxSel / 2) {
-        int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
-        int hi = lo + stride;
-        bool ascending = ((lo & size) == 0);
-        double sl = sel_score[lo], sh = sel_score[hi];
-        uint32_t il = sel_idx[lo], ih = sel_idx[hi];
-        bool hi_before_lo = (sh > sl) || (sh == sl && ih < il);
-        bool lo_before_hi = (sl > sh) || (sl == sh && il < ih);
-        bool swap = ascending ? hi_before_lo : lo_before_hi;
-        if (swap) { sel_score[lo] = sh; sel_score[hi] = sl; sel_idx[lo] = ih; sel_idx[hi] = il; }
-      }
-      __syncthreads();
+  // 5. order by (score desc, idx asc) without barriers: every survivor counts the survivors that precede it, P
+  //    threads per survivor (the pairs are distinct, so the ranks are a permutation), and writes its own output row
+  const int nout = min(nsel, a.k);
+  int n2 = 32;
+  while (n2 < nsel) n2 <<= 1;
+  const int P = kFinalThreads / n2;   // 2 .. 16 threads per survivor, adjacent lanes
+  const int e = tid / P, part = tid - e * P;
+  int rank = 0;
+  double se = 0.0;
+  uint32_t ie = 0;
+  if (e < nsel) {
+    se = sel_score[e];
+    ie = sel_idx[e];
+    for (int j = part; j < nsel; j += P) {
+      const double sj = sel_score[j];
+      const uint32_t ij = sel_idx[j];
+      rank += (sj > se || (sj == se && ij < ie)) ? 1 : 0;
+    }
+  }
+  for (int sh = 1; sh < P; sh <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, sh);
+  if (e < nsel && part == 0 && rank < nout) {
+    const size_t o = (size_t)q * a.k + rank;
+    a.out_ids[o] = a.id_base + (int64_t)ie;
+    a.out_scores[o] = se;
+    if (rank == nout - 1 && a.out_gap) {
+      // every chunk that was not re-scored has a tensor-core score <= the K'-th best key's
+      a.out_gap[q] = m > a.ksel ? (float)(se - (double)key_score((uint64_t)s_minkey)) : CUDART_INF_F;
     }
   }
 
-  // 6. outputs
-  const int nout = min(nsel, a.k);
+  // 6. padding, count
   if (tid == 0) {
     a.out_count[q] = nout;
-    if (a.out_gap) {
-      // every chunk that was not re-scored has a tensor-core score <= score(T)
-      float gap = CUDART_INF_F;
-      if (m > a.ksel && nout > 0) gap = (float)(sel_score[nout - 1] - (double)key_score(T));
-      a.out_gap[q] = gap;
-    }
+    if (a.out_gap && nout == 0) a.out_gap[q] = CUDART_INF_F;
   }
-  for (int i = tid; i < a.k; i += kFinalThreads) {
-    size_t o = (size_t)q * a.k + i;
-    a.out_ids[o] = i < nout ? a.id_base + (int64_t)sel_idx[i] : -1;
-    a.out_scores[o] = i < nout ? sel_score[i] : -CUDART_INF;
+  for (int i = nout + tid; i < a.k; i += kFinalThreads) {
+    const size_t o = (size_t)q * a.k + i;
+    a.out_ids[o] = -1;
+    a.out_scores[o] = -CUDART_INF;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Seed select: a lower bound of each query's corpus-wide K'-th best score from the (uncompacted) lists of
-// the seed pass.  Two-level histogram over the orderable score bits (12 + 8 bits): tau = lower edge of the
-// bin in which the running count from the top reaches K', one ulp lower so that the filter's strict ">"
+// the seed pass: tau = the K'-th best score of the sample, one ulp lower so that the filter's strict ">"
 // keeps ties.  At least K' sample chunks score above tau, so the corpus-wide K'-th best does too.
+//
+// The lists are read ONCE (they are ~100 MB per batch and do not stay in L2): a strided subsample (the first
+// few entries of every list) gives a rough cut r under which about 4 K' of the sample's scores are expected;
+// the one pass over all entries keeps those >= r (a few hundred) in shared memory, and the K'-th best of the
+// kept ones is exact.  When the cut turns out useless (fewer than K' kept: an unrepresentative subsample; or more
+// than the buffer holds: massive ties) the kernel falls back to a two-level histogram over all entries (12 + 8
+// bits, two more passes), whose bound is the lower edge of a 20-bit bin — looser, still a valid lower bound.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dense_seed_select_kernel(const uint64_t* cand, const int32_t* cnt,
-                                                                int n_clusters, int Bpad, int ksel, float* tau_out) {
+constexpr int kSelThreads = 512;
+constexpr int kSelBuf = 4096;   // subsample, then the kept scores (orderable u32)
+
+// want-th largest (1-based, want <= n) of v[0..n) in shared memory, by the whole CTA: MSD radix select, 8 bits a pass.
+__device__ uint32_t cta_kth_largest_u32(const uint32_t* v, int n, int want, uint32_t* hist, uint32_t* s_pref,
+                                        int* s_want) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { *s_pref = 0; *s_want = want; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = *s_pref;
+    for (int i = tid; i < n; i += kSelThreads) {
+      const uint32_t key = v[i];
+      const bool match = ((uint64_t)key >> (shift + 8)) == ((uint64_t)prefix >> (shift + 8));
+      if (match) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int w = *s_want;
+      int d, above;
+      if (radix_find_digit(hist, w, tid, &d, &above)) {
+        *s_want = w - above;
+        *s_pref = prefix | ((uint32_t)d << shift);
+      }
+    }
+    __syncthreads();
+  }
+  return *s_pref;
+}
+
+__global__ void __launch_bounds__(kSelThreads) dense_seed_select_kernel(const uint64_t* cand, const int32_t* cnt,
+                                                                        int n_clusters, int Bpad, int ksel,
+                                                                        float* tau_out) {
+  __shared__ uint32_t buf[kSelBuf];
   __shared__ uint32_t hist[4096];
   __shared__ uint32_t part[256];
-  __shared__ uint32_t s_bin, s_above;
+  __shared__ int s_n[kMaxClusters];
+  __shared__ uint32_t s_pref, s_bin, s_above;
+  __shared__ int s_want, s_total, s_nsub, s_keep;
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t prefix = 0, above = 0;
-  bool enough = true;
-  for (int level = 0; level < 2 && enough; ++level) {
-    const int nb = level == 0 ? 4096 : 256;
-    for (int i = tid; i < nb; i += 256) hist[i] = 0;
-    __syncthreads();
-    for (int c = warp; c < n_clusters; c += 8) {
-      const int n = min(cnt[(size_t)c * Bpad + q], kCap);
-      const uint64_t* src = cand + ((size_t)c * Bpad + q) * kCap;
-      for (int i = lane; i < n; i += 32) {
-        const uint32_t o = f32_orderable(__uint_as_float((uint32_t)(src[i] >> 32)));
-        if (level == 0) atomicAdd(&hist[o >> 20], 1u);
-        else if ((o >> 20) == prefix) atomicAdd(&hist[(o >> 12) & 255u], 1u);
+  if (tid == 0) { s_total = 0; s_nsub = 0; s_keep = 0; }
+  __syncthreads();
+  const int per = kSelBuf / n_clusters;   // subsample: the first `per` entries of every list
+  for (int c = tid; c < n_clusters; c += kSelThreads) {
+    const int n = min(cnt[(size_t)c * Bpad + q], kCap);
+    s_n[c] = n;
+    atomicAdd(&s_total, n);
+    atomicAdd(&s_nsub, min(n, per));
+  }
+  __syncthreads();
+  const int total = s_total, nsub = s_nsub;
+  float tau = -CUDART_INF_F;
+  if (total >= ksel) {   // else: fewer than K' candidates in the whole sample, no bound
+    // scores of list c, entry i (the high word of the raw 8-byte key)
+    auto score_bits = [&](int c, int i) -> uint32_t {
+      return f32_orderable(__uint_as_float((uint32_t)(cand[((size_t)c * Bpad + q) * kCap + i] >> 32)));
+    };
+    // 1. the rough cut: the R-th best of the subsample, R such that ~4 K' of all entries are expected above it
+    uint32_t r = 0;
+    if (total > kSelBuf / 2) {
+      for (int j = tid; j < n_clusters * per; j += kSelThreads) {
+        const int c = j / per, i = j - c * per;
+        buf[j] = i < s_n[c] ? score_bits(c, i) : 0u;   // holes: the smallest key
       }
+      __syncthreads();
+      long long R = (4ll * ksel * nsub + total - 1) / total;
+      if (R < 1) R = 1;
+      if (R > nsub) R = nsub;
+      r = cta_kth_largest_u32(buf, n_clusters * per, (int)R, hist, &s_pref, &s_want);
+      __syncthreads();
     }
-    __syncthreads();
-    // suffix sums: thread t owns bins [t*per, (t+1)*per); find the bin where the count from the top reaches ksel
-    const int per = nb / 256;
-    uint32_t mine = 0;
-    for (int j = 0; j < per; ++j) mine += hist[tid * per + j];
-    part[tid] = mine;
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t cum = above;
-      int t = 255;
-      for (; t >= 0; --t) {
-        if (cum + part[t] >= (uint32_t)ksel) break;
-        cum += part[t];
-      }
-      if (t < 0) { s_bin = 0xffffffffu; s_above = cum; }
-      else {
-        int b = t * per + per - 1;
-        for (; b > t * per; --b) {
-          if (cum + hist[b] >= (uint32_t)ksel) break;
-          cum += hist[b];
+    // 2. one pass over every entry: keep the scores >= r.  A warp per list, eight loads per lane in flight.
+    for (int c = warp; c < n_clusters; c += kSelThreads / 32) {
+      const int n = s_n[c];
+      for (int i0 = lane; i0 < n; i0 += 256) {
+        uint32_t o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = i0 + 32 * u < n ? score_bits(c, i0 + 32 * u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + 32 * u < n && o[u] >= r) {
+            const int slot = atomicAdd(&s_keep, 1);
+            if (slot < kSelBuf) buf[slot] = o[u];
+          }
         }
-        s_bin = (uint32_t)b;
-        s_above = cum;
       }
     }
     __syncthreads();
-    if (s_bin == 0xffffffffu) enough = false;  // fewer than K' candidates in total
-    else if (level == 0) prefix = s_bin;
-    else prefix = (prefix << 8) | s_bin;
-    above = s_above;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    float t = -CUDART_INF_F;
-    if (enough) {
-      const uint32_t edge = prefix << 12;  // 20 significant bits of the orderable score
-      t = f32_from_orderable(edge > 0 ? edge - 1u : 0u);
+    const int kept = s_keep;
+    if (kept >= ksel && kept <= kSelBuf) {
+      // 3. exact: the K'-th best of the kept scores is the K'-th best of the sample
+      const uint32_t v = cta_kth_largest_u32(buf, kept, ksel, hist, &s_pref, &s_want);
+      tau = f32_from_orderable(v > 0 ? v - 1u : 0u);
+    } else {
+      // fallback: two-level histogram over all entries
+      uint32_t prefix = 0, above = 0;
+      bool enough = true;
+      for (int level = 0; level < 2 && enough; ++level) {
+        const int nb = level == 0 ? 4096 : 256;
+        for (int i = tid; i < nb; i += kSelThreads) hist[i] = 0;
+        __syncthreads();
+        for (int c = warp; c < n_clusters; c += kSelThreads / 32) {
+          const int n = s_n[c];
+          for (int i = lane; i < n; i += 32) {
+            const uint32_t o = score_bits(c, i);
+            if (level == 0) atomicAdd(&hist[o >> 20], 1u);
+            else if ((o >> 20) == prefix) atomicAdd(&hist[(o >> 12) & 255u], 1u);
+          }
+        }
+        __syncthreads();
+        // suffix sums: thread t < 256 owns bins [t*per_t, (t+1)*per_t); find the bin where the count from the top
+        // reaches ksel
+        const int per_t = nb / 256;
+        if (tid < 256) {
+          uint32_t mine = 0;
+          for (int j = 0; j < per_t; ++j) mine += hist[tid * per_t + j];
+          part[tid] = mine;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t cum = above;
+          int t = 255;
+          for (; t >= 0; --t) {
+            if (cum + part[t] >= (uint32_t)ksel) break;
+            cum += part[t];
+          }
+          if (t < 0) { s_bin = 0xffffffffu; s_above = cum; }
+          else {
+            int b = t * per_t + per_t - 1;
+            for (; b > t * per_t; --b) {
+              if (cum + hist[b] >= (uint32_t)ksel) break;
+              cum += hist[b];
+            }
+            s_bin = (uint32_t)b;
+            s_above = cum;
+          }
+        }
+        __syncthreads();
+        if (s_bin == 0xffffffffu) enough = false;
+        else if (level == 0) prefix = s_bin;
+        else prefix = (prefix << 8) | s_bin;
+        above = s_above;
+        __syncthreads();
+      }
+      if (enough) {
+        const uint32_t edge = prefix << 12;  // 20 significant bits of the orderable score
+        tau = f32_from_orderable(edge > 0 ? edge - 1u : 0u);
+      }
     }
-    tau_out[q] = t;
   }
+  if (tid == 0) tau_out[q] = tau;
 }
 
 }  // namespace
@@ -626,8 +791,8 @@ template <int G>
 static int launch_score(thr_handle* h, const CUtensorMap& mq, const CUtensorMap& mx, const ScoreArgs& a,
                         cudaStream_t stream, int prof_slot = THR_PROF_DENSE_SCORE) {
   using Cfg = ScoreCfg<G>;
-  THR_CUDA(h, cudaFuncSetAttribute(dense_score_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
+  auto kernel = a.seed_mode ? dense_score_kernel<G, true> : dense_score_kernel<G, false>;
+  THR_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.n_clusters * G);
   cfg.blockDim = dim3(kScoreThreads);
@@ -641,7 +806,7 @@ static int launch_score(thr_handle* h, const CUtensorMap& mq, const CUtensorMap&
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const int tok = thr_prof_begin(h, prof_slot, stream);
-  THR_CUDA(h, cudaLaunchKernelEx(&cfg, dense_score_kernel<G>, mq, mx, a));
+  THR_CUDA(h, cudaLaunchKernelEx(&cfg, kernel, mq, mx, a));
   thr_prof_end(h, tok, stream);
   h->launches++;
   return THR_OK;
@@ -708,6 +873,7 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
   const int64_t tiles = (st->N + kTileN - 1) / kTileN;
   int n_clusters = h->num_sms / G;
   if ((int64_t)n_clusters > tiles) n_clusters = (int)tiles;
+  THR_REQUIRE(h, n_clusters <= kMaxClusters, "thr_dense_topk: %d clusters exceed %d", n_clusters, kMaxClusters);
   const int Bpad = (B + 255) & ~255;
   const size_t cand_bytes = (size_t)n_clusters * Bpad * kCap * sizeof(uint64_t);
   const size_t cnt_bytes = (size_t)n_clusters * Bpad * sizeof(int32_t);
@@ -749,17 +915,16 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
     ScoreArgs sa = a;
     sa.N = seed_rows;
     sa.seed_mode = 1;
-    THR_CUDA(h, cudaMemsetAsync(a.cnt, 0, cnt_bytes, s));
     rc = (G == 2) ? launch_score<2>(h, map_q, st->map_x, sa, s, THR_PROF_DENSE_SEED)
                   : launch_score<1>(h, map_q, st->map_x, sa, s, THR_PROF_DENSE_SEED);
     if (rc != THR_OK) return rc;
     const int tok0 = thr_prof_begin(h, THR_PROF_DENSE_SEED, s);
-    dense_seed_select_kernel<<<B, 256, 0, s>>>(a.cand, a.cnt, n_clusters, Bpad, k + margin, tau_seed);
+    dense_seed_select_kernel<<<B, kSelThreads, 0, s>>>(a.cand, a.cnt, n_clusters, Bpad, k + margin, tau_seed);
     thr_prof_end(h, tok0, s);
     THR_CHECK_LAUNCH(h, "dense_seed_select_kernel");
     a.tau_init = tau_seed;
   }
-  THR_CUDA(h, cudaMemsetAsync(a.cnt, 0, cnt_bytes, s));
+  // (no clearing of a.cnt between the passes: every cluster writes the count of every valid query row on its way out)
   rc = (G == 2) ? launch_score<2>(h, map_q, st->map_x, a, s) : launch_score<1>(h, map_q, st->map_x, a, s);
   if (rc != THR_OK) return rc;
 

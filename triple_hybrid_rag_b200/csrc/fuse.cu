@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
           bool swap = ascending ? id_before(y, x) : id_before(x, y);
           if (swap) { grp[lo] = y; grp[hi] = x; }
         }
-        __syncthreads();
+        bitonic_stage_sync(size, stride, P2, 32);
       }
     }
   }
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(FuseArgs a) {
         bool swap = ascending ? before(y, x) : before(x, y);
         if (swap) { perm[lo] = y; perm[hi] = x; }
       }
-      __syncthreads();
+      bitonic_stage_sync(size, stride, P, 32);
     }
   }
 
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_ranked_kernel(const int32_t
         bool swap = ascending ? before(y, x) : before(x, y);
         if (swap) { perm[a] = y; perm[b] = x; }
       }
-      __syncthreads();
+      bitonic_stage_sync(size, stride, P, 32);
     }
   }
   for (int i = tid; i < n; i += kFuseThreads) out_order[lo + i] = perm[i];
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const double* scores, const 
           int64_t ti = s_id[lo]; s_id[lo] = s_id[hi]; s_id[hi] = ti;
         }
       }
-      __syncthreads();
+      bitonic_stage_sync(size, stride, P, 32);
     }
   }
   int nout = min(s_total, k_out);
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gath
           int64_t ti = s_id[lo]; s_id[lo] = s_id[hi]; s_id[hi] = ti;
         }
       }
-      __syncthreads();
+      bitonic_stage_sync(size, stride, P, 32);
     }
   }
   if (row < B) {

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kRerankMaxC) rerank_finish_kernel(const Finish
         const bool i_first = ki > kj || (ki == kj && pi < pj);   // i belongs before j in the final order
         if (desc ? !i_first : i_first) { s_key[i] = kj; s_key[j] = ki; s_pos[i] = pj; s_pos[j] = pi; }
       }
-      __syncthreads();
+      bitonic_stage_sync(size, stride, kRerankMaxC, 16);
     }
   }
   const int src = s_pos[tid];                       // the candidate that lands at position tid
