@@ -288,7 +288,10 @@ int thr_merge_topk(thr_handle* h, const double* scores, const int64_t* ids,
  * (thr_bm25_topk output), padded with (-inf, -1).  thr_exchange_pack writes it in one launch;
  * thr_exchange_merge consumes the all-gathered buffer [G][msg bytes] and writes both channels' merged
  * lists in the formats thr_dense_topk / thr_bm25_topk use, so thr_fuse runs on them unchanged.
- * New with sharding; same ordering as thr_merge_topk: (score desc, id asc).
+ * New with sharding; same ordering as thr_merge_topk: (score desc, id asc).  Every rank's lists must
+ * arrive in that order (thr_dense_topk and thr_bm25_topk write them so): the merge places an entry at its position
+ * in its own list plus the number of entries that precede it in the other ranks' lists (binary searches), it does
+ * not sort.  G <= 64.
  */
 int64_t thr_exchange_msg_bytes(int B, int k_sem, int k_lex);
 int thr_exchange_pack(thr_handle* h, const int64_t* d_ids, const double* d_sc, const int32_t* d_cnt,

@@ -98,14 +98,14 @@ def test_merge_with_short_lists(engine):
     assert m_id[0].tolist() == [10, 3, 7, 11] and m_sc[0].tolist() == [3.0, 2.0, 2.0, 1.0] and int(m_ct[0]) == 4
 
 
-def test_fused_exchange_matches_the_torch_statement(engine):
+@pytest.mark.parametrize("G,B,k_sem,k_lex", [(3, 7, 10, 6), (8, 5, 100, 100), (2, 3, 100, 37)])
+def test_fused_exchange_matches_the_torch_statement(engine, G, B, k_sem, k_lex):
     """K5 around the all-gather: thr_exchange_pack / thr_exchange_merge against pipeline.exchange_topk (the
     same step stated with torch ops, which the gloo test drives) with the oracle merge standing in for K5.
     G ranks are simulated in one process: every 'rank' packs its own lists, the messages are concatenated."""
     from oracle import merge as omg
     dev = engine.device
     g = torch.Generator().manual_seed(5)
-    G, B, k_sem, k_lex = 3, 7, 10, 6
     k = max(k_sem, k_lex)
     ranks = []
     for r in range(G):
@@ -116,6 +116,14 @@ def test_fused_exchange_matches_the_torch_statement(engine):
         l_sc = torch.randint(1, 6, (B, k_lex), generator=g).float().sort(dim=1, descending=True).values
         d_ids = torch.randperm(B * k_sem * G, generator=g)[: B * k_sem].view(B, k_sem) * G + r
         l_ids = torch.randperm(B * k_lex * G, generator=g)[: B * k_lex].view(B, k_lex) * G + r
+        # a rank's lists arrive sorted by (score desc, id asc), as thr_dense_topk / thr_bm25_topk write them
+        # (thr_exchange_merge merges by rank and relies on it): order the ids inside every run of equal scores
+        def by_id_within_ties(sc_, ids_):
+            o = np.stack([np.lexsort((ids_[b].numpy(), -sc_[b].numpy())) for b in range(sc_.shape[0])])
+            o = torch.from_numpy(o)
+            return torch.gather(sc_, 1, o), torch.gather(ids_, 1, o)
+        d_sc, d_ids = by_id_within_ties(d_sc, d_ids)
+        l_sc, l_ids = by_id_within_ties(l_sc, l_ids)
         ranks.append((d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt))
     nbytes = engine.exchange_msg_bytes(B, k_sem, k_lex)
     assert nbytes == 2 * (2 * B * k * 8) + 2 * B * 4

@@ -548,7 +548,6 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gath
                                                              unsigned long long seq, thr_dev_status* status) {
   __shared__ double s_sc[kMergeMax];
   __shared__ int64_t s_id[kMergeMax];
-  __shared__ int s_total;
   const int row = blockIdx.x, tid = threadIdx.x;
   if (sig) {
     if (tid < G) {   // bounded wait: a rank that never arrives surfaces as THR_ETIMEOUT, not as a hung GPU
@@ -566,68 +565,75 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(const uint8_t* gath
     }
     __syncthreads();
   }
+  // Every rank's list is sorted already (score desc, id asc): merge by RANK instead of sorting — an entry's place in
+  // the merged list is its place in its own list plus, for every other list, the number of entries that precede it
+  // there (a binary search).  No exchange network, no barrier between the staging and the output.
   const int n = G * k;
   const size_t nrow = (size_t)2 * B * k;
-  int P = 32;
-  while (P < n) P <<= 1;
-  if (tid == 0) s_total = 0;
-  __syncthreads();
-  int local = 0;
-  for (int i = tid; i < P; i += 256) {
-    double s = -INFINITY;
-    int64_t id = INT64_MAX;
-    if (i < n) {
-      const int g = i / k, j = i % k;
-      const uint8_t* m = gathered + (size_t)g * msg_bytes;
-      const int cnt = __ldcg((const int32_t*)(m + 2 * nrow * 8) + row);   // L2 is the point of coherence for peer stores
-      if (j < cnt) {
-        s = __ldcg((const double*)m + (size_t)row * k + j);
-        id = (int64_t)__ldcg((const long long*)(m + nrow * 8) + (size_t)row * k + j);
-        ++local;
-      }
-    }
-    s_sc[i] = s;
-    s_id[i] = id;
+  __shared__ int s_cnt[64];
+  if (tid < G) {
+    const uint8_t* m = gathered + (size_t)tid * msg_bytes;
+    s_cnt[tid] = min(max(__ldcg((const int32_t*)(m + 2 * nrow * 8) + row), 0), k);   // L2 is the point of coherence for peer stores
   }
-  if (local) atomicAdd(&s_total, local);
   __syncthreads();
-  auto before = [&](int x, int y) -> bool {
-    int64_t ix = s_id[x], iy = s_id[y];
-    bool vx = ix != INT64_MAX, vy = iy != INT64_MAX;
-    if (vx != vy) return vx;
-    double sx = s_sc[x], sy = s_sc[y];
-    if (sx != sy) return sx > sy;
-    return ix < iy;
-  };
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (P >> 1); i += 256) {
-        int lo = ((i / stride) * (stride << 1)) + (i % stride);
-        int hi = lo + stride;
-        bool ascending = ((lo & size) == 0);
-        bool swap = ascending ? before(hi, lo) : before(lo, hi);
-        if (swap) {
-          double ts = s_sc[lo]; s_sc[lo] = s_sc[hi]; s_sc[hi] = ts;
-          int64_t ti = s_id[lo]; s_id[lo] = s_id[hi]; s_id[hi] = ti;
-        }
+  for (int i = tid; i < n; i += 256) {
+    const int g = i / k, j = i - g * k;
+    if (j < s_cnt[g]) {
+      const uint8_t* m = gathered + (size_t)g * msg_bytes;
+      s_sc[i] = __ldcg((const double*)m + (size_t)row * k + j);
+      s_id[i] = (int64_t)__ldcg((const long long*)(m + nrow * 8) + (size_t)row * k + j);
+    }
+  }
+  __syncthreads();
+  int total = 0;
+  for (int g = 0; g < G; ++g) total += s_cnt[g];
+  const int k_out = row < B ? k_sem : k_lex;
+  const int nout = min(total, k_out);
+  for (int i = tid; i < n; i += 256) {
+    const int g = i / k, j = i - g * k;
+    if (j >= s_cnt[g] || j >= nout) continue;   // an entry's merged place is at least its place in its own list
+    const double s = s_sc[i];
+    const int64_t id = s_id[i];
+    int rank = j;
+    for (int g2 = 0; g2 < G && rank < nout; ++g2) {
+      if (g2 == g) continue;
+      // entries of list g2 that precede (s, id); equal (score, id) pairs cannot come from two ranks of a sharded
+      // corpus — if they ever do, the lower rank goes first, so the merged places stay a permutation
+      int lo = 0, hi = s_cnt[g2];
+      const double* sc2 = s_sc + g2 * k;
+      const int64_t* id2 = s_id + g2 * k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double sm = sc2[mid];
+        const int64_t im = id2[mid];
+        const bool before = sm > s || (sm == s && (im < id || (im == id && g2 < g)));
+        if (before) lo = mid + 1; else hi = mid;
       }
-      bitonic_stage_sync(size, stride, P, 32);
+      rank += lo;
+    }
+    if (rank < nout) {
+      if (row < B) {
+        d_sc[(size_t)row * k_sem + rank] = s;
+        d_ids[(size_t)row * k_sem + rank] = id;
+      } else {
+        const int q = row - B;
+        l_sc[(size_t)q * k_lex + rank] = (float)s;
+        l_ids[(size_t)q * k_lex + rank] = id;
+      }
     }
   }
   if (row < B) {
-    const int nout = min(s_total, k_sem);
     if (tid == 0) d_cnt[row] = nout;
-    for (int i = tid; i < k_sem; i += 256) {
-      d_sc[(size_t)row * k_sem + i] = i < nout ? s_sc[i] : -INFINITY;
-      d_ids[(size_t)row * k_sem + i] = i < nout ? s_id[i] : -1;
+    for (int i = nout + tid; i < k_sem; i += 256) {
+      d_sc[(size_t)row * k_sem + i] = -INFINITY;
+      d_ids[(size_t)row * k_sem + i] = -1;
     }
   } else {
     const int q = row - B;
-    const int nout = min(s_total, k_lex);
     if (tid == 0) l_cnt[q] = nout;
-    for (int i = tid; i < k_lex; i += 256) {
-      l_sc[(size_t)q * k_lex + i] = i < nout ? (float)s_sc[i] : 0.f;
-      l_ids[(size_t)q * k_lex + i] = i < nout ? s_id[i] : -1;
+    for (int i = nout + tid; i < k_lex; i += 256) {
+      l_sc[(size_t)q * k_lex + i] = 0.f;
+      l_ids[(size_t)q * k_lex + i] = -1;
     }
   }
 }
@@ -758,6 +764,7 @@ int thr_exchange_merge_pushed(thr_handle* h, const void* gathered, const uint64_
   if (B == 0) return THR_OK;
   const int k = k_sem > k_lex ? k_sem : k_lex;
   THR_REQUIRE(h, (int64_t)G * k <= kMergeMax, "thr_exchange_merge: G*k = %lld exceeds %d", (long long)G * k, kMergeMax);
+  THR_REQUIRE(h, G <= 64, "thr_exchange_merge: %d ranks exceed 64", G);
   THR_REQUIRE(h, k_sem <= 256 && k_lex <= 256, "thr_exchange_merge: k > 256");
   THR_REQUIRE(h, gathered && d_ids && d_sc && d_cnt && l_ids && l_sc && l_cnt, "thr_exchange_merge: NULL argument");
   THR_REQUIRE(h, ((uintptr_t)gathered & 7u) == 0, "thr_exchange_merge: buffer must be 8-byte aligned");
