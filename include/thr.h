@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define THR_ABI_VERSION 9
+#define THR_ABI_VERSION 10
 
 enum {
   THR_OK = 0,
@@ -79,6 +79,9 @@ enum {
   THR_PROF_SLOTS = 10
 };
 int thr_prof_enable(thr_handle* h, int on);
+/* Time only the slots whose bit is set in `mask` (bit s = slot s; default: all).  An event pair costs ~3 us of
+ * stream time: bench.py times the roofline kernels inside the timed region and the small ones in a pass of their own. */
+int thr_prof_select(thr_handle* h, unsigned mask);
 int thr_prof_reset(thr_handle* h);
 int thr_prof_read(thr_handle* h, int slot, double* total_ms, int64_t* launches);
 

@@ -5,7 +5,6 @@ bash scripts/gpu_tests.sh tests/test_gpu_rerank.py tests/test_gpu_hybrid_rag1.py
 echo "tests rc=$?"; grep -E "^== |passed|failed|error" gpurun_out/r02z_tests_summary.log | tail -40
 python __graft_entry__.py smoke 2>&1 | tail -1
 bash scripts/profile_round.sh r02 > gpurun_out/r02z_profile.log 2>&1; tail -4 gpurun_out/r02z_profile.log
-{ python scripts/maxsim_probe.py 64 1000 32 128; python scripts/maxsim_probe.py 64 1000 128 128; python scripts/maxsim_probe.py 64 1000 32 64; } > gpurun_out/r02z_maxsim_probe.log 2>&1; cat gpurun_out/r02z_maxsim_probe.log
 { python scripts/bm25_probe.py 10000000 256; python scripts/bm25_probe.py 1250000 256; python scripts/bm25_probe.py 1000000 1024; THR_PROBE_COLD=1 python scripts/bm25_probe.py 10000000 256; } 2>&1 | grep docs= > gpurun_out/r02z_bm25_probe.log; cat gpurun_out/r02z_bm25_probe.log
 timeout 1200 python bench.py --steps 30 --warmup 3 > gpurun_out/r02z_bench_n1.json 2> gpurun_out/r02z_bench_n1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r02z_bench_n1.json
-timeout 1200 python bench.py --impl reference --gpus 1 --steps 5 --warmup 1 > gpurun_out/r02z_reference.json 2> gpurun_out/r02z_reference.err; echo "ref rc=$?"; tail -c 400 gpurun_out/r02z_reference.json
+[ -n "$WITH_REFERENCE" ] && { timeout 1200 python bench.py --impl reference --gpus 1 --steps 5 --warmup 1 > gpurun_out/r02z_reference.json 2> gpurun_out/r02z_reference.err; echo "ref rc=$?"; tail -c 400 gpurun_out/r02z_reference.json; }

@@ -18,7 +18,7 @@ THR_EINVAL, THR_ECUDA, THR_EUNSUPPORTED, THR_ENOINDEX, THR_EOVERFLOW, THR_ETIMEO
 FUSE_RAG2, FUSE_LIB, FUSE_RAG1 = 0, 1, 2
 TIE_INSERTION, TIE_CHUNK_ID = 0, 1
 BM25_REQUIRE_ALL = 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 PROF_SLOTS = ("dense_score", "dense_finalize", "bm25", "fuse", "maxsim", "merge", "safety", "bm25_prep", "dense_seed", "rerank")
 
 _p, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -32,6 +32,7 @@ SIGNATURES = {
     "thr_sync": (_i, [_p, _p]),
     "thr_launch_count": (_i64, [_p]),
     "thr_prof_enable": (_i, [_p, _i]),
+    "thr_prof_select": (_i, [_p, C.c_uint]),
     "thr_prof_reset": (_i, [_p]),
     "thr_prof_read": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "thr_dense_index_set": (_i, [_p, _p, _i64, _i, _i64]),

@@ -18,13 +18,13 @@ int thr_fail(thr_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
-void* thr_scratch(thr_handle* h, size_t bytes) {
-  if (bytes <= h->scratch_bytes) return h->scratch;
-  if (h->scratch) {
+void* thr_scratch(thr_handle* h, int arena, size_t bytes) {
+  if (bytes <= h->scratch_bytes[arena]) return h->scratch[arena];
+  if (h->scratch[arena]) {
     cudaDeviceSynchronize();  // previous users may still be in flight
-    cudaFree(h->scratch);
-    h->scratch = nullptr;
-    h->scratch_bytes = 0;
+    cudaFree(h->scratch[arena]);
+    h->scratch[arena] = nullptr;
+    h->scratch_bytes[arena] = 0;
   }
   size_t want = bytes + (bytes >> 2);
   void* p = nullptr;
@@ -33,13 +33,13 @@ void* thr_scratch(thr_handle* h, size_t bytes) {
     thr_fail(h, THR_ENOMEM, "cudaMalloc(%zu) for scratch failed: %s", want, cudaGetErrorString(e));
     return nullptr;
   }
-  h->scratch = p;
-  h->scratch_bytes = want;
+  h->scratch[arena] = p;
+  h->scratch_bytes[arena] = want;
   return p;
 }
 
 int thr_prof_begin(thr_handle* h, int slot, cudaStream_t s) {
-  if (!h->prof_on || h->prof_n >= kProfMax) return -1;
+  if (!h->prof_on || h->prof_n >= kProfMax || !((h->prof_mask >> slot) & 1u)) return -1;
   int i = h->prof_n++;
   h->prof_slot[i] = (unsigned char)slot;
   cudaEventRecord(h->prof_ev[2 * i], s);
@@ -108,6 +108,7 @@ int thr_create(int device, thr_handle** out) {
   thr_handle* h = (thr_handle*)calloc(1, sizeof(thr_handle));
   if (!h) return thr_fail(nullptr, THR_ENOMEM, "thr_create: out of host memory");
   h->device = device;
+  h->prof_mask = 0xffffffffu;
   h->num_sms = prop.multiProcessorCount;
   e = cudaHostAlloc((void**)&h->h_status, sizeof(thr_dev_status), cudaHostAllocMapped);
   if (e == cudaSuccess) {
@@ -129,7 +130,8 @@ int thr_destroy(thr_handle* h) {
   cudaDeviceSynchronize();
   thr_dense_state_free(h);
   thr_bm25_state_free(h);
-  if (h->scratch) cudaFree(h->scratch);
+  for (int i = 0; i < 2; ++i)
+    if (h->scratch[i]) cudaFree(h->scratch[i]);
   if (h->prof_ev) {
     for (int i = 0; i < 2 * kProfMax; ++i) cudaEventDestroy(h->prof_ev[i]);
     free(h->prof_ev);
@@ -150,6 +152,12 @@ int thr_prof_enable(thr_handle* h, int on) {
     for (int i = 0; i < 2 * kProfMax; ++i) THR_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
   }
   h->prof_on = on ? 1 : 0;
+  return THR_OK;
+}
+
+int thr_prof_select(thr_handle* h, unsigned mask) {
+  if (!h) return THR_EINVAL;
+  h->prof_mask = mask;
   return THR_OK;
 }
 

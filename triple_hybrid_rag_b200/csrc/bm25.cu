@@ -671,7 +671,8 @@ __global__ void __launch_bounds__(1024) bm25_plan_kernel(const int32_t* q_terms,
   __syncthreads();
   unsigned long long part = 0;
   for (int q = tid; q < B; q += 1024) part += (keys[q] >> 32) + kRangeCost * (unsigned long long)n_blk;
-  atomicAdd(&s_tot, part);
+  for (int sh = 16; sh > 0; sh >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sh);
+  if ((tid & 31) == 0 && part) atomicAdd(&s_tot, part);   // one shared-memory atomic per warp, not per thread
   __syncthreads();
   unsigned long long target = s_tot / (unsigned long long)num_slots + 1;
   if (target < 16384ull) target = 16384ull;
@@ -937,7 +938,7 @@ static int bm25_topk_impl(thr_handle* h, const int32_t* q_terms, const int32_t* 
   const size_t o_tau = o_pkeys + up(max_units * (size_t)k * 8);
   const size_t o_wl = o_tau + up((size_t)B * 4);
   const size_t need = o_wl + up((size_t)grid * warps * kListCap * 8);
-  uint8_t* ws = (uint8_t*)thr_scratch(h, need);
+  uint8_t* ws = (uint8_t*)thr_scratch(h, 1, need);
   if (!ws) return THR_ENOMEM;
   unsigned long long* keys = (unsigned long long*)(ws + o_keys);
   Unit* units = (Unit*)(ws + o_units);

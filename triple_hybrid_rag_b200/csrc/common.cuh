@@ -33,10 +33,11 @@ struct thr_handle {
   thr_dev_status* h_status;  // pinned, mapped host memory: still readable after a trapped kernel
   thr_dense_state* dense;
   thr_bm25_state* bm25;
-  void* scratch;             // generic device scratch (grown on demand)
-  size_t scratch_bytes;
+  void* scratch[2];          // device scratch, grown on demand: one arena per channel (0 dense, 1 BM25), so that the two
+  size_t scratch_bytes[2];   // channels of one batch may run on different streams at the same time
   // per-kernel timing (thr_prof_*): ring of event pairs
   int prof_on;
+  unsigned prof_mask;        // slots that are timed (thr_prof_select; all by default)
   int prof_n;
   cudaEvent_t* prof_ev;      // [2 * kProfMax]
   unsigned char* prof_slot;  // [kProfMax]
@@ -47,8 +48,8 @@ int thr_prof_begin(thr_handle* h, int slot, cudaStream_t s);
 void thr_prof_end(thr_handle* h, int token, cudaStream_t s);
 
 int thr_fail(thr_handle* h, int code, const char* fmt, ...);
-// Grow-only device scratch owned by the handle. Returns NULL (and sets err) on failure.
-void* thr_scratch(thr_handle* h, size_t bytes);
+// Grow-only device scratch owned by the handle (arena 0: dense, 1: BM25). Returns NULL (and sets err) on failure.
+void* thr_scratch(thr_handle* h, int arena, size_t bytes);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed).
 int thr_encode_tma_2d_bf16(thr_handle* h, CUtensorMap* map, const void* base, uint64_t rows,
                            uint64_t cols, uint32_t box_rows, uint32_t box_cols);

@@ -877,7 +877,7 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
   const int Bpad = (B + 255) & ~255;
   const size_t cand_bytes = (size_t)n_clusters * Bpad * kCap * sizeof(uint64_t);
   const size_t cnt_bytes = (size_t)n_clusters * Bpad * sizeof(int32_t);
-  uint8_t* ws = (uint8_t*)thr_scratch(h, cand_bytes + cnt_bytes + (size_t)Bpad * sizeof(float));
+  uint8_t* ws = (uint8_t*)thr_scratch(h, 0, cand_bytes + cnt_bytes + (size_t)Bpad * sizeof(float));
   if (!ws) return THR_ENOMEM;
 
   CUtensorMap map_q;

@@ -70,6 +70,11 @@ class Engine:
         self._check(self._lib.thr_prof_enable(self._h, int(on)))
         self._check(self._lib.thr_prof_reset(self._h))
 
+    def prof_select(self, names=None):
+        """Time only the named slots (_lib.PROF_SLOTS names; None: all)."""
+        mask = 0xffffffff if names is None else sum(1 << _lib.PROF_SLOTS.index(n) for n in names)
+        self._check(self._lib.thr_prof_select(self._h, mask))
+
     def prof_read(self) -> dict:
         """{kernel: (total_ms, launches)} since prof_enable/prof_reset; synchronises the device."""
         out = {}

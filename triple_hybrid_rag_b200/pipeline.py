@@ -116,6 +116,12 @@ class TripleHybridSearcher:
         self._pinned = {}
         self._offs = {}
         self.exchange_fallback = None   # why the pushed exchange is not in use (None: it is, or world == 1)
+        # K1 and K2 on two streams (THR_OVERLAP=1 or .overlap = True; default: one after the other on the caller's
+        # stream).  Measured: -4 to -7 % per step on a 1.25M-chunk shard, -1 to -3 % at 10M — off by default
+        # because CUDA events around a kernel stop measuring that kernel once another chain shares the SMs, and the
+        # bench's roofline accounting rests on exactly those events.
+        self.overlap = os.environ.get("THR_OVERLAP", "0") == "1"
+        self._side = None
 
     # ---- index residency -------------------------------------------------------------------
     def set_dense(self, X_local: torch.Tensor, id_base: int = 0):
@@ -172,8 +178,28 @@ class TripleHybridSearcher:
         dense_error_bound; `certify` does it on the host)."""
         eng, dev = self.engine, self.engine.device
         B = Q.shape[0]
-        d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin, want=want)
-        l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex, want=want, require_all=require_all)
+        if self.overlap:
+            # The two channels do not depend on each other: K2's chain (plan, range kernel, unit merge) goes on a
+            # second stream and K1's (seed, select, score, finalize) on a high-priority one.  Both big kernels take
+            # whole SMs, so they still run one after the other — but each one's tail is filled by the other chain,
+            # and the small kernels of one chain run beside the other chain's big kernel.  K1's CTAs win when both
+            # are ready (its tile partition is static: a late cluster would delay the whole kernel; K2's CTAs take
+            # work from a queue and do not care when they start).  The engine keeps one scratch arena per channel.
+            main = torch.cuda.current_stream(dev)
+            s_dense, s_lex = self._streams()
+            s_dense.wait_stream(main)
+            s_lex.wait_stream(main)
+            with torch.cuda.stream(s_lex):
+                l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex, want=want, require_all=require_all)
+            with torch.cuda.stream(s_dense):
+                d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin, want=want)
+            main.wait_stream(s_dense)
+            main.wait_stream(s_lex)
+            for t in (l_ids, l_sc, l_cnt, d_ids, d_sc, d_cnt, gap):   # allocated on the side streams, consumed on `main`
+                t.record_stream(main)
+        else:
+            d_ids, d_sc, d_cnt, gap = eng.dense_topk(Q, k_sem, margin, want=want)
+            l_ids, l_sc, l_cnt = eng.bm25_topk(q_terms, q_off, k_lex, want=want, require_all=require_all)
         if self.world > 1:
             d_ids, d_sc, d_cnt, l_ids, l_sc, l_cnt = self._exchange(B, k_sem, k_lex, d_ids, d_sc, d_cnt,
                                                                     l_ids, l_sc, l_cnt)
@@ -191,6 +217,11 @@ class TripleHybridSearcher:
         ids, rrf, ranks, _, cnt = eng.fuse(_lib.FUSE_RAG2, B, [lex_list, sem_list, gr_list], weights, rrf_k=rrf_k,
                                            top_k=top_k, max_out=top_k, tie_mode=tie_mode)
         return SearchOutput(ids, rrf, ranks, cnt, d_ids, d_sc, l_ids, l_sc, l_cnt, gap)
+
+    def _streams(self):
+        if self._side is None:
+            self._side = (torch.cuda.Stream(self.engine.device, priority=-1), torch.cuda.Stream(self.engine.device, priority=0))
+        return self._side
 
     def _as_csr(self, ids: torch.Tensor, cnt: torch.Tensor):
         """A fixed-width [B,k] result is already CSR with stride k: thr_fuse skips the -1 padding."""
