@@ -30,7 +30,7 @@ for r in rows[start + 1:]:
 steps, cur = [], None
 for i, (k, v) in enumerate(L):
     if cur is None:
-        if k.endswith('<2>') and i + 1 < len(L) and L[i + 1][0].startswith('dense_seed_select'):
+        if 'dense_score_kernel<2' in k and i + 1 < len(L) and L[i + 1][0].startswith('dense_seed_select'):
             cur = [(k, v)]
     else:
         cur.append((k, v))
@@ -55,7 +55,7 @@ print("belong to the BM25-alone loop and the batch-1 latency loop (`dense_score_
 print("| kernel | launches/step | avg µs | share of step |\n|---|---|---|---|")
 for k, v in agg.items():
     print(f"| `{k}` | {len(v) // n} | {sum(v) / len(v):.1f} | {100 * sum(v) / n / tot:.1f}% |")
-print(f"\nsum per step under ncu: {tot / 1e3:.2f} ms.  dense_score_kernel appears twice per step: the seed pass (prefix, ~0.1 ms) and the full pass.")
+print(f"\nsum per step under ncu: {tot / 1e3:.2f} ms.  `dense_score_kernel<2, 1>` is the seed pass (prefix), `<2, 0>` the full pass.")
 b = json.load(open(bench))
 st = b['stages_ms']
 s = sum(st.values())
