@@ -415,3 +415,40 @@ class _SkipPlanning:
 
     def retrieve(self, query, collection=None, top_k=None):
         return self.r.retrieve(query, collection=collection, top_k=top_k, skip_planning=True)
+
+
+def test_index_from_exported_table_rows(engine, settings):
+    """the corpus as the reference stores it (rag_child_chunks / rag_documents / rag_parent_chunks rows,
+    vectors rendered as text) -> export.from_tables -> ResidentIndex gives the same channel lists as the index built
+    from the same chunks directly, and the collection predicate follows the DOCUMENT's collection."""
+    from triple_hybrid_rag_b200.export import from_tables
+    n, D = 600, 128
+    chunks, emb, parents = _corpus(n, D, seed=11)
+    doc_coll = {}
+    for c in chunks:                      # one collection per document, as in rag_documents
+        doc_coll.setdefault(c["document_id"], c["collection"])
+        c["collection"] = doc_coll[c["document_id"]]
+    child_rows = [{"id": c["child_id"], "parent_id": c["parent_id"], "document_id": c["document_id"], "org_id": "o1",
+                   "index_in_parent": i % 4, "text": c["text"], "page": c["page"], "modality": c["modality"],
+                   "content_hash": f"h{i}", "embedding_1024": "[" + ",".join(repr(float(x)) for x in emb[i]) + "]"}
+                  for i, c in enumerate(chunks)]
+    child_rows.append({**child_rows[0], "id": "foreign", "org_id": "o2"})
+    doc_rows = [{"id": d, "org_id": "o1", "collection": col} for d, col in doc_coll.items()]
+    parent_rows = [{"id": pid, "text": p["text"], "section_heading": p["section_heading"]} for pid, p in parents.items()]
+    t_chunks, t_emb, t_parents, st = from_tables(child_rows, doc_rows, parent_rows, org_id="o1")
+    assert st.children_kept == n and st.other_org == 1 and torch.equal(t_emb, emb)
+    qv = emb[77] + 0.2 * torch.randn(D, generator=torch.Generator().manual_seed(1))
+    out = []
+    for ch, em, pa in ((chunks, emb, parents), (t_chunks, t_emb, t_parents)):
+        ix = ResidentIndex(engine, ch, em, pa, blk_docs=256)
+        r = GpuRAG2Retriever(org_id="o1", embedder=_Embedder({"q": qv.tolist()}), query_planner=MagicMock(), index=ix,
+                             graph_enabled=False, lexical_match="any")
+        sem = asyncio.run(r._semantic_search("q", "a", 40))
+        lex = asyncio.run(r._lexical_search(["w2", "w9", "w40"], "b", 40))
+        cands = asyncio.run(r._expand_to_parents([R.RetrievalCandidate(child_id=x["child_id"], parent_id=x["parent_id"],
+                                                                       document_id=x["document_id"], text=x["text"],
+                                                                       page=x["page"], modality=x["modality"])
+                                                  for x in sem[:3]]))
+        out.append((sem, lex, [(c.parent_text, c.section_heading) for c in cands]))
+    assert out[0] == out[1] and len(out[0][0]) == 40 and out[0][1]
+    assert all(doc_coll[x["document_id"]] == "a" for x in out[1][0]) and all(doc_coll[x["document_id"]] == "b" for x in out[1][1])

@@ -1,6 +1,7 @@
 """Host logic of the BM25 index builder (no GPU): layout invariants of include/thr.h, agreement with
 the oracle's term-major CSR, and concat(parts) == build(whole)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import bm25 as ob
@@ -96,3 +97,73 @@ def test_pad_dim_keeps_dot_products():
     p = pad_dim(x)
     assert p.shape == (5, 4032) and torch.equal(p[:, :4000], x) and not p[:, 4000:].any()
     assert torch.equal(pad_dim(p), p)
+
+
+def _table_rows(n=20, D=8, seed=3):
+    """Rows as the reference's ingest writes them (src/voice_agent/rag2/ingest.py:434-449) and as PostgREST returns
+    them: uuid-like strings, the vector as text."""
+    g = np.random.default_rng(seed)
+    docs = [{"id": f"doc-{j}", "org_id": "org-1", "collection": ["contracts", "policies", None][j % 3], "title": f"t{j}"}
+            for j in range(4)]
+    parents = [{"id": f"par-{j}", "document_id": f"doc-{j // 2}", "org_id": "org-1", "index_in_document": j % 2,
+                "text": f"parent text {j}", "section_heading": f"h{j}" if j % 2 else None} for j in range(8)]
+    children = []
+    for i in range(n):
+        v = g.standard_normal(D).astype(np.float32)
+        children.append({"id": f"ch-{i}", "parent_id": f"par-{i % 8}", "document_id": f"doc-{(i % 8) // 2}",
+                         "org_id": "org-1", "index_in_parent": i // 8, "text": f"texto numero {i}", "token_count": 3,
+                         "page": 1 + i % 5, "modality": "table" if i % 7 == 0 else "text", "content_hash": f"h{i}",
+                         "metadata": {}, "embedding_1024": "[" + ",".join(repr(float(x)) for x in v) + "]",
+                         "_vec": v})
+    return children, docs, parents
+
+
+def test_export_from_table_rows():
+    """rag_child_chunks / rag_documents / rag_parent_chunks rows -> ResidentIndex inputs, with the
+    predicates of the search RPCs (20260114_rag2_schema.sql:366-370): one org, the document's collection."""
+    from triple_hybrid_rag_b200.export import from_tables, parse_pgvector
+    children, docs, parents = _table_rows()
+    children.append({**children[0], "id": "ch-other", "org_id": "org-2"})          # another tenant's row
+    children.append({**children[1], "id": "ch-orphan", "document_id": "doc-gone"})  # its document row is missing
+    children.append(dict(children[2]))                                               # the same primary key twice
+    chunks, X, pmap, st = from_tables(children, docs, parents, org_id="org-1")
+    assert st.children_seen == 23 and st.children_kept == 20 and st.other_org == 1 and st.unknown_document == 1
+    assert st.duplicate_ids == 1 and st.dim == 8 and X.shape == (20, 8) and X.dtype == torch.float32
+    for i, c in enumerate(chunks):
+        src = children[i]
+        assert c["child_id"] == src["id"] and c["parent_id"] == src["parent_id"] and c["document_id"] == src["document_id"]
+        assert c["text"] == src["text"] and c["page"] == src["page"] and c["modality"] == src["modality"]
+        assert c["collection"] == docs[(i % 8) // 2]["collection"]          # the DOCUMENT's collection
+        assert np.array_equal(X[i].numpy(), src["_vec"])                    # text rendering round-trips float32 exactly
+    assert set(pmap) == {f"par-{j}" for j in range(8)} and pmap["par-3"] == {"id": "par-3", "text": "parent text 3",
+                                                                             "section_heading": "h3"}
+    assert st.collections == {"contracts": 10, "policies": 6, None: 4}
+    # vector renderings
+    assert parse_pgvector(None) is None and parse_pgvector("null") is None
+    assert np.array_equal(parse_pgvector([1, 2.5]), np.array([1, 2.5], dtype=np.float32))
+    assert np.array_equal(parse_pgvector(" (1, -2) "), np.array([1, -2], dtype=np.float32))
+    with pytest.raises(ValueError):
+        parse_pgvector("[1,2,3]", dim=4)
+    with pytest.raises(ValueError):
+        parse_pgvector([1.0, float("nan")])
+
+
+def test_export_missing_embeddings_and_jsonl(tmp_path):
+    import json
+    from triple_hybrid_rag_b200.export import from_tables, read_jsonl
+    children, docs, parents = _table_rows(n=6)
+    for c in children:
+        c.pop("_vec")
+    children[4]["embedding_1024"] = None
+    with pytest.raises(ValueError, match="ch-4"):
+        from_tables(children, docs, parents)
+    chunks, X, _, st = from_tables(children, docs, parents, missing_embedding="drop")
+    assert [c["child_id"] for c in chunks] == ["ch-0", "ch-1", "ch-2", "ch-3", "ch-5"] and st.missing_embedding == 1
+    chunks, X, _, st = from_tables(children, docs, parents, missing_embedding="zero")
+    assert len(chunks) == 6 and float(X[4].abs().sum()) == 0.0 and float(X[3].abs().sum()) > 0
+    # without document rows the chunk's own `collection` key (if the export denormalised it) is used
+    chunks, _, _, _ = from_tables([{**children[0], "collection": "x"}])
+    assert chunks[0]["collection"] == "x"
+    p = tmp_path / "children.jsonl"
+    p.write_text("\n".join(json.dumps(c) for c in children) + "\n\n", encoding="utf-8")
+    assert read_jsonl(p) == children
