@@ -97,3 +97,38 @@ def test_bm25_full_size_properties(engine):
     m_sc, m_id, m_ct = engine.merge_topk(g_sc, g_id, g_ct, K)
     engine.sync()
     assert torch.equal(m_id, ids) and torch.equal(m_sc.float().view(torch.int32), sc.view(torch.int32))
+
+
+def test_two_stream_search_equals_single_stream(engine):
+    """TripleHybridSearcher.overlap (K1's and K2's kernel chains on two streams, one scratch arena per channel) must not
+    change a bit of the step's output: fused lists, both channel lists, counts and the dense certificate, over several
+    steps with different query batches, on a corpus large enough for the seed pass and multi-range BM25 units."""
+    from triple_hybrid_rag_b200.pipeline import TripleHybridSearcher
+    dev = engine.device
+    n, G = 1_048_576, 262144
+    X = synth.dense_rows(0, n, D, device=dev)
+    parts = []
+    for gb in range(n // G):
+        doc, term, tf, L = synth.bm25_block_coo(gb, G, V=V, device=dev)
+        parts.append(BM25Index.build(doc, term, tf, L, V, blk_docs=2048, avgdl=200.0, idf=torch.zeros(V)))
+    idf = bm25_idf(sum(p.df for p in parts), n)
+    index = BM25Index.concat(parts, idf=idf)
+    s = TripleHybridSearcher(engine)
+    s.set_dense(X)
+    s.set_bm25(index)
+    outs = {False: [], True: []}
+    for step in range(3):
+        Q = synth.dense_queries(B, D, X, n_plant=n // (2 + step))
+        qt, qo = pack_queries(synth.bm25_queries(B, V=V, seed=100 + step), dev)
+        for ov in (False, True, True, False):
+            s.overlap = ov
+            o = s.search(Q, qt, qo, None, k_sem=K, k_lex=K, top_k=K)
+            engine.sync()
+            outs[ov].append([t.clone() for t in (o.ids, o.rrf, o.count, o.sem_ids, o.sem_scores, o.lex_ids, o.lex_scores,
+                                                 o.lex_count, o.gap)])
+    s.overlap = False
+    assert len(outs[True]) == len(outs[False]) == 6
+    for a, b in zip(outs[False], outs[True]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert int(outs[True][0][2].min()) == K
