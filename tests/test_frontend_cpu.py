@@ -71,3 +71,42 @@ def test_a_failing_batch_fails_every_waiter():
                                     return_exceptions=True)
     res = asyncio.run(go())
     assert len(res) == 3 and all(isinstance(r, RuntimeError) and "libthr" in str(r) for r in res)
+
+
+# ---- the tool boundary's response dictionary, against the reference's own function ---------------------------------
+def test_tool_response_matches_the_reference_goldens():
+    """format_tool_response / search_knowledge_base_rag2 == what the reference's `_search_knowledge_base_rag2`
+    (crm_knowledge.py:126-182, run unmodified by tests/golden/make_tool_golden.py) returned for the same
+    RetrievalResult: refusals, empty results, missing parent text, falsy scores, tables."""
+    import json
+    from pathlib import Path
+    from triple_hybrid_rag_b200.retriever import RetrievalCandidate, RetrievalResult
+    from triple_hybrid_rag_b200.tool import format_tool_response, search_knowledge_base_rag2
+    cases = json.loads((Path(__file__).parent / "golden" / "tool_golden.json").read_text(encoding="utf-8"))
+    assert len(cases) == 8
+    for case in cases:
+        r = case["result"]
+        result = RetrievalResult(success=r["success"], contexts=[RetrievalCandidate(**c) for c in r["contexts"]],
+                                 max_rerank_score=r["max_rerank_score"], refused=r["refused"],
+                                 refusal_reason=r["refusal_reason"], timings=dict(r["timings"]))
+        assert format_tool_response(case["query"], case["category"], result) == case["response"]
+
+        class Stub:
+            async def retrieve(self, query, collection=None, top_k=None):
+                assert (query, collection, top_k) == (case["query"], case["category"], case["limit"])
+                return result
+        assert search_knowledge_base_rag2(case["query"], case["category"], case["limit"], retriever=Stub()) == case["response"]
+
+
+def test_blocking_tool_handler_refuses_a_running_loop():
+    import asyncio
+    from triple_hybrid_rag_b200.tool import search_knowledge_base_rag2
+
+    class Stub:
+        async def retrieve(self, query, collection=None, top_k=None):
+            return None
+
+    async def inside():
+        with pytest.raises(RuntimeError, match="blocking tool handler"):
+            search_knowledge_base_rag2("q", retriever=Stub())
+    asyncio.run(inside())
