@@ -110,3 +110,31 @@ def test_blocking_tool_handler_refuses_a_running_loop():
         with pytest.raises(RuntimeError, match="blocking tool handler"):
             search_knowledge_base_rag2("q", retriever=Stub())
     asyncio.run(inside())
+
+
+def test_fallback_planner_matches_the_reference_goldens():
+    """FallbackQueryPlanner == the plan the reference's QueryPlanner returns when its LLM call fails
+    (query_planner.py:178-187; goldens: tests/golden/make_planner_golden.py), field for field, defaults included."""
+    import asyncio
+    import dataclasses
+    import json
+    from pathlib import Path
+    from triple_hybrid_rag_b200.retriever import FallbackQueryPlanner
+    cases = json.loads((Path(__file__).parent / "golden" / "planner_golden.json").read_text(encoding="utf-8"))
+    assert len(cases) == 10
+    p = FallbackQueryPlanner()
+    for case in cases:
+        assert dataclasses.asdict(p.plan(case["query"], case["collection"])) == case["plan"]
+        assert dataclasses.asdict(asyncio.run(p.plan_async(case["query"], case["collection"]))) == case["plan"]
+
+
+def test_settings_defaults_match_the_reference():
+    """Rag2Settings() == the reference's default rag2_* retrieval knobs (config.py:280-314; golden written by
+    tests/golden/make_planner_golden.py from the reference's Settings class)."""
+    import json
+    from pathlib import Path
+    from triple_hybrid_rag_b200.retriever import Rag2Settings
+    want = json.loads((Path(__file__).parent / "golden" / "settings_golden.json").read_text(encoding="utf-8"))
+    mine = Rag2Settings()
+    have = {k: getattr(mine, k) for k in dir(mine) if k.startswith("rag2_")}
+    assert have == want and all(type(have[k]) is type(want[k]) for k in want)
