@@ -14,9 +14,10 @@ eng.prof_enable(True)
 for _ in range(10):
     eng.dense_topk(Q, 100, 28)
 eng.sync()
-tot = {1: [], 2: [], 3: []}
+TILES = tuple(int(x) for x in os.environ.get('THR_PROBE_TILES', '2,3,4').split(','))
+tot = {t: [] for t in TILES}
 for rep in range(4):
-    for t in (1, 2, 3):
+    for t in TILES:
         os.environ["THR_DENSE_SEED_TILES"] = str(t)
         eng.dense_index_set(X)      # the knob is read when the index is set (no getenv on the hot path)
         eng.dense_topk(Q, 100, 28); eng.sync(); eng.prof_reset()
@@ -25,6 +26,6 @@ for rep in range(4):
         p = eng.prof_read()
         per_call = (p["dense_score"][0] + p["dense_seed"][0] + p["dense_finalize"][0]) / 6
         tot[t].append(per_call)
-for t in (1, 2, 3):
+for t in TILES:
     print(f"N={N} tiles {t}: score+seed+finalize per call {sorted(tot[t])[len(tot[t]) // 2]:.3f} ms (runs: " +
           " ".join(f"{x:.3f}" for x in tot[t]) + ")")

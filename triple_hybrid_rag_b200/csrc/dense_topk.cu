@@ -36,7 +36,8 @@ constexpr int kMaxSel = 256;       // largest K' = k + margin
 constexpr int kScoreThreads = 192;
 constexpr int kFinalThreads = 512;
 constexpr int kMaxClusters = 160;    // finalize / seed select: clusters of one launch (<= SMs / cta_group), a multiple of 32
-constexpr int kSeedTiles = 3;      // tiles per cluster in the seed pass: 3 x 256 candidates fit a list without compaction
+constexpr int kSeedTiles = 3;      // tiles per cluster in the seed pass (default for large shards)
+constexpr int kSeedTilesMax = kCap / kTileN;   // 4 x 256 candidates fill a list exactly; the lists stay uncompacted
 
 template <int G> struct ScoreCfg {
   // measured at 10M x 1536, B = 256: 4 stages 6.54 ms, 5 stages 6.17 ms, 7 stages 6.26 ms
@@ -58,7 +59,7 @@ struct ScoreArgs {
   uint64_t* cand;   // [n_clusters][Bpad][kCap]
   int32_t* cnt;     // [n_clusters][Bpad]
   const float* tau_init;  // [Bpad] nullable: per-query lower bound of the K'-th best score (seed pass)
-  int seed_mode;          // seed pass: leave the lists uncompacted (<= kSeedTiles * kTileN entries each)
+  int seed_mode;          // seed pass: leave the lists uncompacted (<= kSeedTilesMax * kTileN entries each)
   const uint16_t* tags;   // [N] nullable: per-chunk tag (collection id) for filtered queries
   const int32_t* want;    // [B] nullable: tag a query's chunks must carry, < 0 = any
   thr_dev_status* status;
@@ -832,7 +833,7 @@ int thr_dense_index_set(thr_handle* h, const void* X, int64_t N, int D, int64_t 
   if (env && env[0] == '1') st->cta_group = 1;
   env = getenv("THR_DENSE_SEED_TILES");
   st->seed_tiles = env ? atoi(env) : 0;
-  if (st->seed_tiles > kSeedTiles) st->seed_tiles = kSeedTiles;
+  if (st->seed_tiles > kSeedTilesMax) st->seed_tiles = kSeedTilesMax;
   env = getenv("THR_DENSE_NO_SEED");
   st->no_seed = env && env[0] == '1';
   h->dense = st;
@@ -904,7 +905,7 @@ int thr_dense_topk_tagged(thr_handle* h, const void* Q, int B, int k, int margin
   // Seed pass: score a small prefix of the corpus first and start the full pass from its K'-th best
   // score.  Every cluster then filters with a threshold learnt from ~130k chunks from its first tile on
   // (instead of from -inf), which cuts the epilogue's append work and list compactions several-fold.
-  // tiles per cluster in the seed pass (<= kSeedTiles: the uncompacted lists must fit): a longer prefix gives a
+  // tiles per cluster in the seed pass (<= kSeedTilesMax: the uncompacted lists must fit): a longer prefix gives a
   // tighter threshold but costs its own scoring and a select over n_clusters * tiles * 256 scores per query
   const int seed_tiles_env = st->seed_tiles;   // THR_DENSE_SEED_TILES, read when the index was set
   // measured at D = 1536, B = 256 (score + seed, ms): 1.25M rows 0.897 / 0.854 / 0.915 for 1 / 2 / 3 tiles,
