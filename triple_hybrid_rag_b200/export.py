@@ -21,7 +21,7 @@ pgvector values arrive as text ("[0.12,-0.5,...]", PostgREST's rendering), as li
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
+from typing import Any, Dict, Iterable, List, Mapping, Optional, Tuple
 
 import numpy as np
 import torch

@@ -12,7 +12,6 @@ reference's tool layer (CRM glue: out of scope)."""
 from __future__ import annotations
 
 import asyncio
-import functools
 import time
 from typing import Any, Dict, List, Optional
 
