@@ -47,7 +47,8 @@ for st in steps:
     for k, v in st:
         agg.setdefault(k, []).append(v)
 tot = sum(sum(v) for v in agg.values()) / n
-print("# ncu launch list (command: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline`, 10M x 1536, B=256)\n")
+what = sys.argv[3] if len(sys.argv) > 3 else "`python bench.py --steps 3 --warmup 3 --no-cpu-baseline`, 10M x 1536, B=256"
+print(f"# ncu launch list (command: {what})\n")
 print("`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch times are cold-cache and serialised; compare SHARES.")
 print(f"Launch 0 is `bm25_df_kernel` (index registration); then {per} launches per step; the table averages the {n} batch-256")
 print(f"steps of the run (warm-up, timed and end-to-end steps do the same work).  The last launches in `{src.split('/')[-1]}`")
